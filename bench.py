@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- constraint + Jacobian evals/sec of the Bezier hot path on B200.
+
+Workload (BASELINE.json configs[3], "C4"): synthetic 1024-vehicle 3-D swarm,
+degree 10, DEG_ELEV 100: one *eval* = the full constraint vector of one x
+(523 776 pairs x 121 separation values + 1024 x 121 max-speed values = 508 MB).
+One *step* = one pass over a batch of B such x (the base point and B-1
+finite-difference perturbations of it, which is what SLSQP's Jacobian asks for).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU).  Sharding: the batch of
+perturbed x is split across ranks (each rank evaluates its own B x over all
+pairs, no data-path collective); the per-pair minimum (the active-pair source,
+[B, P] fp64) is all-gathered over NCCL/NVLink so every rank holds the whole
+min-distance matrix.  Weak scaling: B per rank is fixed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(N=1024, dim=3, deg=10, elev=100)
+SEED = 20261018
+
+
+def synthetic_swarm(N, deg, seed=SEED):
+    """SURVEY 8(d) 'Synthetic inputs C4' (same generator as oracle/make_golden.py)."""
+    rng = np.random.default_rng(seed)
+    init = rng.uniform(0, 100, size=(N, 3))
+    final = rng.uniform(0, 100, size=(N, 3))
+    args = dict(numVeh=N, dimension=3, degree=deg, minimizeGoal='Euclidean',
+                maxSep=0.9, maxSpeed=5, tf=20.0, initPoints=init, finalPoints=final)
+    x = np.empty((N * 3, deg - 1))
+    for i in range(N):
+        for d in range(3):
+            x[3 * i + d] = np.linspace(init[i, d], final[i, d], deg + 1)[1:-1]
+    x = x + rng.normal(size=x.shape)
+    return args, x.ravel()
+
+
+def fd_batch(x, B, seed=1):
+    """base x plus B-1 single-variable forward perturbations (SciPy's h)."""
+    X = np.repeat(x[None, :], B, axis=0)
+    rng = np.random.default_rng(seed)
+    for b, k in enumerate(rng.choice(x.size, size=B - 1, replace=False), start=1):
+        X[b, k] += 1.4901161193847656e-08
+    return X
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+def cpu_port_worker(task):
+    """Oracle port (numpy restatement of the reference) on a block of pairs."""
+    from oracle import bezier_oracle as O
+    y, pairs, dim, maxSep, E = task
+    t0 = time.perf_counter()
+    out = []
+    for (i, j) in pairs:
+        dv = y[i * dim:(i + 1) * dim] - y[j * dim:(j + 1) * dim]
+        out.append(O.elev(O.norm_square(dv), E)[0] - maxSep ** 2)
+    return time.perf_counter() - t0, len(pairs)
+
+
+def cpu_baseline(args, x, E, target_seconds=12.0, procs=None):
+    """Times the oracle port on a bounded sample of the C4 pairs on all host
+    cores and extrapolates to evals/s (pairs are independent and equal cost)."""
+    import multiprocessing as mp
+    from oracle import bezier_oracle as O
+    procs = procs or os.cpu_count() or 1
+    m = O.Model(**args)
+    y = O.reshape_vector(m, x)
+    N, dim = m.numVeh, m.dim
+    P = N * (N - 1) // 2
+    rng = np.random.default_rng(0)
+    # calibrate on one core
+    cal = [(int(a), int(b)) for a, b in zip(rng.integers(0, N // 2, 200), rng.integers(N // 2, N, 200))]
+    O.elev(O.norm_square(y[:dim] - y[dim:2 * dim]), E)      # warm tables
+    tcal, _ = cpu_port_worker((y, cal, dim, m.maxSep, E))
+    per_pair = tcal / len(cal)
+    n_per_proc = max(200, int(target_seconds / per_pair))
+    tasks = []
+    for p in range(procs):
+        ii = rng.integers(0, N - 1, n_per_proc)
+        jj = np.minimum(ii + 1 + rng.integers(0, N - 1, n_per_proc) % np.maximum(N - 1 - ii, 1), N - 1)
+        tasks.append((y, list(zip(ii.tolist(), jj.tolist())), dim, m.maxSep, E))
+    t0 = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(cpu_port_worker, tasks)
+    else:
+        res = [cpu_port_worker(tasks[0])]
+    wall = time.perf_counter() - t0
+    pairs_done = sum(r[1] for r in res)
+    pairs_per_s = pairs_done / wall
+    # one eval = P pairs (+ N speed rows, same per-row cost as a pair)
+    evals_per_s = pairs_per_s / (P + N)
+    return {"value": evals_per_s, "unit": "evals/s", "cores": procs, "kind": "port",
+            "sample": "%d of %d pairs of the C4 swarm (N=%d, deg %d, elev %d) on %d processes, "
+                      "%.1f s wall; numpy restatement of the reference (oracle/bezier_oracle.py), "
+                      "extrapolated linearly in pairs" % (pairs_done, P, N, m.deg, E, procs, wall)}, wall
+
+
+# --------------------------------------------------------------------------
+def run_reference(opts):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    args, x = synthetic_swarm(WORKLOAD["N"], WORKLOAD["deg"])
+    E = WORKLOAD["elev"]
+    vals, walls = [], []
+    per_step = max(2.0, min(20.0, 120.0 / max(1, opts.steps + opts.warmup)))
+    for s in range(opts.warmup + opts.steps):
+        cb, wall = cpu_baseline(args, x, E, target_seconds=per_step)
+        if s >= opts.warmup:
+            vals.append(cb["value"])
+            walls.append(wall)
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {"impl": "reference", "metric": "constraint+Jacobian evals/sec", "value": v, "unit": "evals/s",
+            "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
+            "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(1), "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(B):
+    return {"workload": "C4 synthetic swarm: N=1024 vehicles, dim 3, degree 10, DEG_ELEV 100, "
+                        "all 523776 pairs x 121 separation values + 1024 x 121 max-speed values per eval",
+            "evals_per_step_per_gpu": B, "sharding": "FD-perturbation batch split across ranks; "
+            "all-gather of the [B,P] per-pair minimum", "l2_policy": "outputs (508 MB/eval) >> 126 MB L2, "
+            "streaming stores; inputs 270 KB"}
+
+
+# --------------------------------------------------------------------------
+def run_ours(opts):
+    import torch
+    import torch.distributed as dist
+    from optimalbeziertrajectorygeneration_b200 import optimization as gopt
+    from optimalbeziertrajectorygeneration_b200.engine import num_pairs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    N, deg, E = WORKLOAD["N"], WORKLOAD["deg"], WORKLOAD["elev"]
+    B = opts.batch
+    args, x = synthetic_swarm(N, deg)
+    Xall = fd_batch(x, B * world)
+    X = Xall[rank * B:(rank + 1) * B]
+    bezopt = gopt.BezOptimization(**args)
+    eng = bezopt._engine(True)
+    P = num_pairs(N)
+    L = 2 * deg + E + 1
+    d_x = eng.upload(X)
+    out_sep = torch.empty((B, P, L), dtype=torch.float64, device=eng.device)
+    out_spd = torch.empty((B, N, L), dtype=torch.float64, device=eng.device)
+    pairmin = torch.empty((B, P), dtype=torch.float64, device=eng.device)
+    gathered = torch.empty((world * B, P), dtype=torch.float64, device=eng.device) if world > 1 else None
+    max_speed2 = float(args["maxSpeed"]) ** 2
+
+    def step():
+        cpts, tf = eng.assemble(d_x, E)
+        eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pairmin)
+        eng.speed(cpts, tf, E, -1.0, max_speed2, out=out_spd)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pairmin)
+    launches_per_step = 4       # assemble, pair kernel, pair-min kernel, speed kernel
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, opts.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(opts.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # dominant kernel alone (pair kernel), CUDA events on its stream
+    cpts, tf = eng.assemble(d_x, E)
+    torch.cuda.synchronize()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(opts.steps)]
+    for a, b_ in kev:
+        a.record()
+        eng.separation(cpts, E, args["maxSep"], out=out_sep)
+        b_.record()
+    torch.cuda.synchronize()
+    kms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the reference-facing closures: host x in, host numpy out
+    e2e = None
+    if rank == 0 or world > 1:
+        gopt.DEG_ELEV = E
+        bezopt.zero_copy_results = True
+        sepf, spdf = bezopt.temporalSeparationConstraints, bezopt.maxSpeedConstraints
+        nE = max(2, min(opts.steps, 4))
+        for _ in range(2):
+            sepf(X[0]); spdf(X[0])
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(nE):
+            r1 = sepf(X[s % B]); r2 = spdf(X[s % B])
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": nE * world / dt, "unit": "evals/s",
+               "h2d_bytes_per_step": int(2 * x.size * 8), "d2h_bytes_per_step": int((r1.size + r2.size) * 8),
+               "evals_timed": nE * world,
+               "note": "BezOptimization.temporalSeparationConstraints(x)+maxSpeedConstraints(x): "
+                       "host x -> pinned H2D -> kernels -> D2H of the full constraint vector into pinned host memory"}
+        gopt.DEG_ELEV = 0
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = json.load(open(peaks_path))["hbm_gbs"]
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = 8.0 * B * (P * L + 2 * 3 * (deg + 1) * N)      # rows written + control points read
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        evals = B * world * opts.steps
+        line = {"metric": "constraint+Jacobian evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s",
+                "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
+                "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(B),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "kernel": "sq_elev_kernel<10,3,PAIR>",
+                             "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                "e2e": e2e, "gpu_launches": launches_per_step * opts.steps, "clocks": clocks}
+        if world == 1 and not opts.no_cpu:
+            cb, _ = cpu_baseline(args, x, E, target_seconds=12.0)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="evals (x vectors) per step per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    opts = ap.parse_args()
+    if opts.impl == "reference":
+        run_reference(opts)
+    else:
+        run_ours(opts)
+
+
+if __name__ == "__main__":
+    main()

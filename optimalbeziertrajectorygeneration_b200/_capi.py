@@ -1,0 +1,79 @@
+"""ctypes binding of libbezgpu.so (include/bezgpu.h).
+
+There is NO CPU fallback: importing this module without the built library, or
+calling into it without a CUDA device, raises.  The library is built in-tree by
+``__graft_entry__.build()`` / ``python -m optimalbeziertrajectorygeneration_b200._build``.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbezgpu.so")
+
+c_double_p = ctypes.c_void_p      # raw device/host addresses (tensor.data_ptr())
+c_plan_p = ctypes.c_void_p
+
+
+class BezGpuError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise BezGpuError(
+            "libbezgpu.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "-- there is no CPU fallback for the Bezier constraint path." % LIB_PATH)
+    return ctypes.CDLL(LIB_PATH)
+
+
+_lib = _load()
+
+I, D, P, L64 = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64
+
+# name -> (restype, argtypes); must list every symbol include/bezgpu.h declares
+SIGNATURES = {
+    "bez_last_error": (ctypes.c_char_p, []),
+    "bez_version": (I, []),
+    "bez_plan_create": (I, [I, I, I, I, P, P, P, ctypes.POINTER(c_plan_p)]),
+    "bez_plan_destroy": (I, [c_plan_p]),
+    "bez_plan_info": (I, [c_plan_p, ctypes.POINTER(I), ctypes.POINTER(I), ctypes.POINTER(I),
+                          ctypes.POINTER(I)]),
+    "bez_assemble_cpts": (I, [c_plan_p, P, I, I, I, I, I, I, I, D,
+                              P, P, P, P, P, P, P, P, P, P, P, P]),
+    "bez_pair_sepsq_elev": (I, [c_plan_p, P, I, I, L64, L64, D, P, P, P]),
+    "bez_speed_sq_elev": (I, [c_plan_p, P, P, I, I, I, I, D, D, P, P]),
+}
+
+OPTIONAL = {}
+
+
+def _bind(table, required):
+    for name, (res, args) in table.items():
+        try:
+            fn = getattr(_lib, name)
+        except AttributeError:
+            if required:
+                raise BezGpuError("libbezgpu.so does not export %s; rebuild it" % name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind(SIGNATURES, True)
+
+
+def last_error():
+    return _lib.bez_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise BezGpuError("%s failed (code %d): %s" % (what, rc, last_error()))
+
+
+def call(name, *args):
+    """Invoke an entry point that returns a status code and raise on failure."""
+    check(getattr(_lib, name)(*args), name)
+
+
+lib = _lib

