@@ -59,55 +59,55 @@ def fd_batch(x, B, seed=1):
 
 # --------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled (NVML) during the timed region."""
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+               "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
+
+    def __init__(self, gpu_index, period=0.02):
+        self.gpu, self.period = gpu_index, period
+        self.sm, self.reasons, self.smax = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:            # pragma: no cover
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [s.strip() for s in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # --------------------------------------------------------------------------
@@ -233,7 +233,7 @@ def run_ours(opts):
         eng.speed(cpts, tf, E, -1.0, max_speed2, out=out_spd)
         if world > 1:
             dist.all_gather_into_tensor(gathered, pairmin)
-    launches_per_step = 4       # assemble, pair kernel, pair-min kernel, speed kernel
+    launches_per_step = 3       # assemble, fused pair kernel (values + per-pair min), speed kernel
 
     def barrier():
         if world > 1:
@@ -265,7 +265,7 @@ def run_ours(opts):
            for _ in range(opts.steps)]
     for a, b_ in kev:
         a.record()
-        eng.separation(cpts, E, args["maxSep"], out=out_sep)
+        eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pairmin)
         b_.record()
     torch.cuda.synchronize()
     kms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
@@ -314,7 +314,7 @@ def run_ours(opts):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(B),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "kernel": "sq_elev_kernel<10,3,PAIR>",
+                             "frac": achieved / peak, "traffic": None, "kernel": "sq_elev_kernel<10,3,PAIR,2,min>",
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": launches_per_step * opts.steps, "clocks": clocks}
         if world == 1 and not opts.no_cpu:

@@ -17,13 +17,13 @@
  *     GJK, minDist, collCheck) are compiled without FMA contraction so that
  *     they reproduce the reference's numba/numpy rounding.
  *
- * Control-point layout in HBM ("SoA"):   cpts[b][d][k][v]
+ * Control-point layout in HBM ("vehicle rows"):   cpts[b][v][S]
  *     b = evaluation point (base or finite-difference perturbed x)   0..B-1
- *     d = spatial dimension                                          0..dim-1
- *     k = control point index                                        0..n
- *     v = vehicle index (vehicles first, then point obstacles)       0..N-1
- * i.e. the vehicle index is the fastest one so that warps that walk over
- * vehicle pairs load 128-byte lines.
+ *     v = curve index (vehicles first, then point obstacles)         0..N-1
+ *     S = dim*(n+1) rounded up to an even count (16-byte aligned rows); entry
+ *         d*(n+1)+k is control point k of dimension d, the pad entry is 0.
+ * A warp that walks over 32 consecutive pairs (i, j..j+31) reads one row
+ * (broadcast) plus one contiguous 32*S*8-byte span with 128-bit loads.
  */
 #ifndef BEZGPU_H
 #define BEZGPU_H
@@ -72,7 +72,7 @@ int bez_plan_info(const bez_plan *plan, int *n, int *dim, int *elev, int *L);
  *   timeopt    0/1 : tf = x[nvar-1] else tf_fixed
  *   d_init/d_final [numVeh][dim]; d_ispeed/d_fspeed/d_icos/d_isin/d_fcos/d_fsin [numVeh]
  *   d_obst     [nObs][dim] (may be NULL when nObs == 0)
- *   d_cpts     [B][dim][n+1][numVeh+nObs]   (output)
+ *   d_cpts     [B][numVeh+nObs][S]          (output)
  *   d_tf       [B]                          (output; the tf each x implies)
  */
 int bez_assemble_cpts(const bez_plan *plan, const double *d_x, int B, int nvar,

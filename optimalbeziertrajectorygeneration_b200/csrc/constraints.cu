@@ -25,10 +25,8 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTile = 256;   // items (pairs / vehicles) per tile == threads per block
-constexpr int kChunk = 4;    // items processed together in stage 2 (ILP)
 
 enum Mode { PAIR = 0, SPEED = 1 };
 
@@ -47,7 +45,7 @@ __host__ __device__ constexpr int widx(int i, int j) {   // i <= j
 }
 
 struct SqElevArgs {
-    const double *cpts;     // [B][dim][n+1][N]
+    const double *cpts;     // [B][N][S]  S = dim*(n+1) rounded up to even
     const double *tf;       // [B] (SPEED)
     const double *PQ;       // [2n+1][LhPad]
     double *out;            // [B][nitems][L]
@@ -55,55 +53,214 @@ struct SqElevArgs {
     long long item_begin;   // first pair / vehicle handled
     long long nitems;       // pairs / vehicles per evaluation point
     int B, N, L, Lh, LhPad;
-    double alpha, beta;     // out = alpha * value + beta
+    double alpha, beta;     // out = alpha * value + beta   (alpha = +-1)
 };
 
-template <int N_, int DIM, int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+// min without fmin()'s NaN bookkeeping (1 DSETP + 2 SEL instead of ~6 instructions)
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+
+// Min over the L outputs of each item: separate pass for the shapes the fused
+// epilogue does not cover (L > 128 or degree < 4).
+__global__ void item_min_kernel(const double *__restrict__ vals, long long nrows, int L,
+                                double *__restrict__ mins) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    const double *r = vals + (size_t)warp * L;
+    double m = INFINITY;
+    for (int i = lane; i < L; i += 32) m = dmin(m, r[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = dmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) mins[warp] = m;
+}
+
+// Shared-memory geometry of one staged item row: SLOTS double2 slots
+// (slot j < n : (e_j, o_j); slot n : (e_n, 0); the rest is padding so that the
+// prefetch ring of depth kRing indexes statically), row stride RS slots with RS
+// odd so that the per-lane 128-bit stores of stage 1 are bank-conflict free.
+constexpr int kRing = 4;
+template <int N_> struct RowGeom {
+    static constexpr int SLOTS = (N_ + 1 + kRing - 1) / kRing * kRing;
+    static constexpr int RS = SLOTS | 1;
+};
+
+// Stage 2 of sq_elev_kernel for one group of 32*CPL column pairs: lane l owns
+// columns col_c = (g*CPL + c)*32 + l and their mirrors M - col_c.  Items are
+// consumed two at a time (8 independent DFMA chains per lane for CPL = 2); their
+// staged rows stream through a kRing-deep register ring refilled kRing slots
+// ahead (LDS latency ~ 14 DFMA issue slots).  FULL = all 32 items of the tile
+// are live: the loop body is then branch free, so the scheduler can overlap the
+// stores of one unit with the DFMAs of the next.
+template <int N_, int CPL, bool WITH_MIN, bool FULL>
+__device__ __forceinline__ void sweep_columns(double2 *rows, const double *tab, double *outb,
+                                              int g, int lane, int cnt, int L, int Lh, int LhPad,
+                                              double beta) {
+    constexpr int NC = N_ + 1;
+    constexpr int SLOTS = RowGeom<N_>::SLOTS;
+    constexpr int RS = RowGeom<N_>::RS;
+    const int M = L - 1;
+    bool live[CPL];
+    double P[CPL][NC], Q[CPL][N_ > 0 ? N_ : 1];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        const int col = (g * CPL + c) * 32 + lane;
+        live[c] = col < Lh;
+        const int tc = col < LhPad ? col : 0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) P[c][j] = tab[j * LhPad + tc];
+#pragma unroll
+        for (int j = 0; j < N_; ++j) Q[c][j] = tab[(NC + j) * LhPad + tc];
+    }
+    // per-lane output cursors: column c sits at fwd + 32*c, its mirror at mir - 32*c
+    // (compile-time displacements); both advance by L per item.  The centre column
+    // of an even-degree result is its own mirror: both stores then write the same
+    // value (its odd part is exactly 0), so no special case is needed.
+    double *fwd = outb + (g * CPL * 32 + lane);
+    double *mir = outb + (M - g * CPL * 32 - lane);
+
+    double2 ra[kRing], rb[kRing];
+#pragma unroll
+    for (int r = 0; r < kRing; ++r) {
+        ra[r] = rows[r];                 // row 0
+        rb[r] = rows[RS + r];            // row 1
+    }
+    for (int p0 = 0; p0 < cnt; p0 += 2) {
+        // rows of the next unit for the wrap-around prefetch (clamped in-bounds)
+        const int pn = (p0 + 2 < 32) ? p0 + 2 : p0;
+        const double2 *rowA = rows + (size_t)p0 * RS;
+        const double2 *rowB = rowA + RS;
+        const double2 *nxtA = rows + (size_t)pn * RS;
+        const double2 *nxtB = nxtA + RS;
+        double se[2][CPL], so[2][CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            se[0][c] = beta; se[1][c] = beta;
+            so[0][c] = 0.0; so[1][c] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            const int r = j % kRing;
+            if (j < N_) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    se[0][c] = fma(ra[r].x, P[c][j], se[0][c]);
+                    so[0][c] = fma(ra[r].y, Q[c][j], so[0][c]);
+                    se[1][c] = fma(rb[r].x, P[c][j], se[1][c]);
+                    so[1][c] = fma(rb[r].y, Q[c][j], so[1][c]);
+                }
+            } else if (j == N_) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    se[0][c] = fma(ra[r].x, P[c][N_], se[0][c]);
+                    se[1][c] = fma(rb[r].x, P[c][N_], se[1][c]);
+                }
+            }
+            const int jn = j + kRing;
+            if (jn < SLOTS) {
+                if (jn <= N_) { ra[r] = rowA[jn]; rb[r] = rowB[jn]; }
+            } else if (jn - SLOTS <= N_) {
+                ra[r] = nxtA[jn - SLOTS]; rb[r] = nxtB[jn - SLOTS];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const bool item_live = FULL || (p0 + u < cnt);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                if (live[c] && item_live) {
+                    __stcs(fwd + 32 * c, se[u][c] + so[u][c]);
+                    __stcs(mir - 32 * c, se[u][c] - so[u][c]);
+                }
+            }
+            fwd += L;
+            mir += L;
+            if (WITH_MIN) {
+                // min(se+so, se-so) == se - |so| bit for bit (one DADD)
+                double mn = live[0] ? se[u][0] - fabs(so[u][0]) : INFINITY;
+#pragma unroll
+                for (int c = 1; c < CPL; ++c)
+                    mn = live[c] ? dmin(mn, se[u][c] - fabs(so[u][c])) : mn;
+                // fold the warp in half, then park the 16 partial minima in the
+                // (already consumed) staged row of this item
+                mn = dmin(mn, __shfl_xor_sync(0xffffffffu, mn, 16));
+                if (lane < 16) reinterpret_cast<double *>(rows + (size_t)(p0 + u) * RS)[lane] = mn;
+            }
+        }
+    }
+}
+
+// One warp = one tile of 32 items.  No block-wide barriers in the main loop: the
+// warps of a block only share the (read-only) staged elevation table.
+//   CPL = column pairs per lane in one sweep (1 or 2): lane l owns columns
+//   {l, l+32}[:CPL] of the current 32*CPL-column group and their mirrors.
+template <int N_, int DIM, int MODE, int CPL, bool WITH_MIN>
+__global__ void __launch_bounds__(kThreads, 3)
 sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N_> DW) {
     constexpr int NC = N_ + 1;
-    constexpr int ROW = 2 * N_ + 2;          // doubles per shared row (16 B aligned)
-    extern __shared__ __align__(16) double smem[];   // [kTile][ROW]
+    constexpr int NT = 2 * N_ + 1;           // table rows
+    constexpr int SLOTS = RowGeom<N_>::SLOTS;
+    constexpr int RS = RowGeom<N_>::RS;
+    static_assert(!WITH_MIN || 2 * RS >= 16, "staged row too short to park 16 partial minima");
+    extern __shared__ __align__(16) double smem[];
+    // layout: [kWarps][32][RS] double2 item rows | [NT][LhPad] table
+    double2 *rows = reinterpret_cast<double2 *>(smem) + (size_t)(threadIdx.x >> 5) * 32 * RS;
+    double *tab = smem + (size_t)kWarps * 32 * RS * 2;
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const long long tiles_per_eval = (A.nitems + kTile - 1) / kTile;
-    const long long ntiles = tiles_per_eval * A.B;
-    const int CG = A.LhPad >> 5;             // column groups of 32
+    const int lane = tid & 31;
+    for (int i = tid; i < NT * A.LhPad; i += kThreads) tab[i] = __ldg(A.PQ + i);
+    __syncthreads();
+
+    const long long wtiles_per_eval = (A.nitems + 31) >> 5;
+    const long long nwt = wtiles_per_eval * A.B;
+    const long long gwarp = (long long)blockIdx.x * kWarps + (tid >> 5);
+    const long long nwarps = (long long)gridDim.x * kWarps;
     const int M = A.L - 1;
-    const size_t bstride = (size_t)DIM * NC * A.N;
+    constexpr int S = (DIM * NC + 1) / 2 * 2;                 // doubles per vehicle row (16 B aligned)
+    const size_t bstride = (size_t)S * A.N;
+    const int ngroups = (A.LhPad / 32 + CPL - 1) / CPL;     // sweeps over the columns
+    const double scale = A.alpha * (0.5 * (double)DIM);       // Q1: dim/2 (sign of alpha folded in)
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b = (int)(tile / tiles_per_eval);
-        const long long t0 = (tile - (long long)b * tiles_per_eval) * kTile;  // first item of tile
-        const int cnt = (int)((A.nitems - t0) < kTile ? (A.nitems - t0) : kTile);
+    for (long long wt = gwarp; wt < nwt; wt += nwarps) {
+        const int b = (int)(wt / wtiles_per_eval);
+        const long long t0 = (wt - (long long)b * wtiles_per_eval) << 5;   // first item of the tile
+        const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
 
-        // ------------------------------ stage 1 ------------------------------
-        if (tid < cnt) {
+        // ------------------------- stage 1: lane = item -------------------------
+        {
+            // lanes past the end recompute the last item so every staged row is finite
+            const int li = lane < cnt ? lane : cnt - 1;
             const double *base = A.cpts + (size_t)b * bstride;
             double a[DIM][NC];
             if (MODE == PAIR) {
                 int vi, vj;
-                bez_pair_decode(A.item_begin + t0 + tid, A.N, vi, vj);
+                bez_pair_decode(A.item_begin + t0 + li, A.N, vi, vj);
+                const double2 *pi = reinterpret_cast<const double2 *>(base + (size_t)vi * S);
+                const double2 *pj = reinterpret_cast<const double2 *>(base + (size_t)vj * S);
+                double *af = &a[0][0];
 #pragma unroll
-                for (int d = 0; d < DIM; ++d)
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        const double *row = base + (size_t)(d * NC + k) * A.N;
-                        a[d][k] = __ldg(row + vi) - __ldg(row + vj);   // Bezier.sub
-                    }
+                for (int q = 0; q < S / 2; ++q) {                      // Bezier.sub
+                    const double2 u = __ldg(pi + q), w = __ldg(pj + q);
+                    if (2 * q < DIM * NC) af[2 * q] = u.x - w.x;
+                    if (2 * q + 1 < DIM * NC) af[2 * q + 1] = u.y - w.y;
+                }
             } else {
-                const int v = (int)(A.item_begin + t0 + tid);
+                const int v = (int)(A.item_begin + t0 + li);
                 const double val = (double)N_ / __ldg(A.tf + b);       // diffMatrix: n/tf
+                const double2 *pv = reinterpret_cast<const double2 *>(base + (size_t)v * S);
+                double ptf[S];
+#pragma unroll
+                for (int q = 0; q < S / 2; ++q) {
+                    const double2 u = __ldg(pv + q);
+                    ptf[2 * q] = u.x;
+                    ptf[2 * q + 1] = u.y;
+                }
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) {
-                    double pt[NC], dd[NC];
-#pragma unroll
-                    for (int k = 0; k < NC; ++k)
-                        pt[k] = __ldg(base + (size_t)(d * NC + k) * A.N + v);
+                    double dd[NC];
 #pragma unroll
                     for (int k = 0; k < N_; ++k)                       // np.dot(cpts, Dm)
-                        dd[k] = pt[k] * (-val) + pt[k + 1] * val;
+                        dd[k] = ptf[d * NC + k] * (-val) + ptf[d * NC + k + 1] * val;
                     dd[N_] = 0.0;
 #pragma unroll
                     for (int k = 0; k < NC; ++k) {                     // .elev(1) back to degree n
@@ -125,81 +282,38 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
                     for (int d = 1; d < DIM; ++d) g = fma(a[d][i], a[d][j], g);
                     s[i + j] = fma(PW.w[widx<N_>(i, j)], g, s[i + j]);
                 }
-            const double scale = 0.5 * (double)DIM;                    // Q1: dim/2
-            double *row = smem + (size_t)tid * ROW;
+            double2 *row = rows + (size_t)lane * RS;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
                 const double lo = s[j] * scale, hi = s[2 * N_ - j] * scale;
-                *reinterpret_cast<double2 *>(row + 2 * j) = make_double2(lo + hi, lo - hi);
+                row[j] = make_double2(lo + hi, lo - hi);
             }
-            *reinterpret_cast<double2 *>(row + 2 * N_) = make_double2(s[N_] * scale, 0.0);
+            row[N_] = make_double2(s[N_] * scale, 0.0);
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ------------------------------ stage 2 ------------------------------
-        {
-            const int nslots = (CG <= kWarps) ? (kWarps / CG) : 1;
-            const int slot = (CG <= kWarps) ? (warp / CG) : 0;
-            if (slot < nslots) {
-                for (int cg = (CG <= kWarps) ? (warp % CG) : warp; cg < CG; cg += kWarps) {
-                    const int col = cg * 32 + lane;
-                    const bool live = col < A.Lh;
-                    const int mcol = M - col;
-                    double P[NC], Q[N_ > 0 ? N_ : 1];
+        // ------------------- stage 2: lane = output column(s) -------------------
+        double *outb = A.out + ((size_t)b * A.nitems + t0) * A.L;
+        for (int g = 0; g < ngroups; ++g) {
+            if (cnt == 32)
+                sweep_columns<N_, CPL, WITH_MIN, true>(rows, tab, outb, g, lane, 32, A.L, A.Lh, A.LhPad, A.beta);
+            else
+                sweep_columns<N_, CPL, WITH_MIN, false>(rows, tab, outb, g, lane, cnt, A.L, A.Lh, A.LhPad, A.beta);
+        }
+        if (WITH_MIN) {
+            __syncwarp();
+            // lane p reduces the 16 partial minima parked in row p
+            const double *mb = reinterpret_cast<const double *>(rows + (size_t)lane * RS);
+            double m0 = mb[0], m1 = mb[1], m2 = mb[2], m3 = mb[3];
 #pragma unroll
-                    for (int j = 0; j < NC; ++j) P[j] = __ldg(A.PQ + (size_t)j * A.LhPad + col);
-#pragma unroll
-                    for (int j = 0; j < N_; ++j) Q[j] = __ldg(A.PQ + (size_t)(NC + j) * A.LhPad + col);
-
-                    double *outb = A.out + ((size_t)b * A.nitems + t0) * A.L;
-                    for (int p0 = slot * kChunk; p0 < cnt; p0 += nslots * kChunk) {
-                        double se[kChunk], so[kChunk];
-#pragma unroll
-                        for (int u = 0; u < kChunk; ++u) {
-                            const int p = (p0 + u < cnt) ? (p0 + u) : (cnt - 1);
-                            const double *row = smem + (size_t)p * ROW;
-                            double e = 0.0, o = 0.0;
-#pragma unroll
-                            for (int j = 0; j < N_; ++j) {
-                                const double2 eo = *reinterpret_cast<const double2 *>(row + 2 * j);
-                                e = fma(eo.x, P[j], e);
-                                o = fma(eo.y, Q[j], o);
-                            }
-                            e = fma(row[2 * N_], P[N_], e);
-                            se[u] = e;
-                            so[u] = o;
-                        }
-#pragma unroll
-                        for (int u = 0; u < kChunk; ++u) {
-                            if (live && p0 + u < cnt) {
-                                double *o = outb + (size_t)(p0 + u) * A.L;
-                                __stcs(o + col, fma(A.alpha, se[u] + so[u], A.beta));
-                                if (mcol != col) __stcs(o + mcol, fma(A.alpha, se[u] - so[u], A.beta));
-                            }
-                        }
-                    }
-                }
+            for (int q = 4; q < 16; q += 4) {
+                m0 = dmin(m0, mb[q]); m1 = dmin(m1, mb[q + 1]);
+                m2 = dmin(m2, mb[q + 2]); m3 = dmin(m3, mb[q + 3]);
             }
+            if (lane < cnt) A.itemmin[(size_t)b * A.nitems + t0 + lane] = dmin(dmin(m0, m1), dmin(m2, m3));
         }
-        __syncthreads();
+        __syncwarp();
     }
-}
-
-// ---------------------------------------------------------------------------
-// Min over the L outputs of each item (active-pair flag source).  Separate,
-// bandwidth-trivial pass used only when the caller asks for it and the fused
-// epilogue is not available.
-__global__ void item_min_kernel(const double *__restrict__ vals, long long nrows, int L,
-                                double *__restrict__ mins) {
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= nrows) return;
-    const double *r = vals + (size_t)warp * L;
-    double m = INFINITY;
-    for (int i = lane; i < L; i += 32) m = fmin(m, r[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) mins[warp] = m;
 }
 
 // ---------------------------------------------------------------------------
@@ -215,17 +329,18 @@ struct AssembleArgs {
 __global__ void assemble_cpts_kernel(const AssembleArgs A) {
     const int NC = A.n + 1;
     const int N = A.numVeh + A.nObs;
-    const long long total = (long long)A.B * A.dim * NC * N;
+    const int S = (A.dim * NC + 1) / 2 * 2;
+    const long long total = (long long)A.B * N * S;
     const int offset = (A.fixed_ends ? 1 : 0) + (A.dubins ? 1 : 0);
     const int ncols = NC - 2 * offset;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx % N);
-        long long r = idx / N;
-        const int k = (int)(r % NC);
-        r /= NC;
-        const int d = (int)(r % A.dim);
-        const int b = (int)(r / A.dim);
+        const int e = (int)(idx % S);
+        const long long r = idx / S;
+        const int v = (int)(r % N);
+        const int b = (int)(r / N);
+        if (e >= A.dim * NC) { A.cpts[idx] = 0.0; continue; }          // alignment pad
+        const int d = e / NC, k = e - d * NC;
         const double *x = A.x + (size_t)b * A.nvar;
         const double tf = A.timeopt ? x[A.nvar - 1] : A.tf_fixed;
         double val;
@@ -248,13 +363,13 @@ __global__ void assemble_cpts_kernel(const AssembleArgs A) {
             val = x[(size_t)(v * A.dim + d) * ncols + (k - offset)];
         }
         A.cpts[idx] = val;
-        if (v == 0 && k == 0 && d == 0) A.tf[b] = tf;
+        if (v == 0 && e == 0) A.tf[b] = tf;
     }
 }
 
 // ---------------------------------------------------------------------------
-template <int N_, int DIM, int MODE>
-int launch_sq_elev(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
+template <int N_, int DIM, int MODE, int CPL, bool WITH_MIN>
+int launch_sq_elev2(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     ProdWeights<N_> PW;
     DiffWeights<N_> DW;
     for (int i = 0; i <= N_; ++i)
@@ -264,21 +379,49 @@ int launch_sq_elev(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
         }
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
 
-    const size_t shmem = (size_t)kTile * (2 * N_ + 2) * sizeof(double);
-    static bool attr_done = false;    // per template instantiation
-    if (!attr_done) {
-        BEZ_CUDA(cudaFuncSetAttribute(sq_elev_kernel<N_, DIM, MODE>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        attr_done = true;
+    const size_t shmem = ((size_t)kWarps * 32 * RowGeom<N_>::RS * 2 + (size_t)(2 * N_ + 1) * A.LhPad) * sizeof(double);
+    if (shmem > 227 * 1024) {
+        bez_set_error("degree %d with elevation %d needs %zu bytes of shared memory (> 227 KB)",
+                      plan->n, plan->elev, shmem);
+        return BEZ_EUNSUPPORTED;
     }
-    int dev = 0, sms = 148;
+    auto kern = sq_elev_kernel<N_, DIM, MODE, CPL, WITH_MIN>;
+    static size_t attr_set = 0;       // per template instantiation
+    if (shmem > attr_set) {
+        BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        attr_set = shmem;
+    }
+    int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long ntiles = ((A.nitems + kTile - 1) / kTile) * A.B;
-    long long grid = (long long)sms * 2;
-    if (grid > ntiles) grid = ntiles;
+    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
+    if (per_sm < 1) per_sm = 1;
+    const long long nwt = ((A.nitems + 31) / 32) * A.B;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (nwt + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
     if (grid < 1) return BEZ_OK;
-    sq_elev_kernel<N_, DIM, MODE><<<(unsigned)grid, kThreads, shmem, st>>>(A, PW, DW);
+    kern<<<(unsigned)grid, kThreads, shmem, st>>>(A, PW, DW);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
+
+template <int N_, int DIM, int MODE>
+int launch_sq_elev(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
+    const bool two = A.LhPad > 32;      // more than one 32-column group: 2 column pairs per lane
+    // the fused per-item minimum parks partial results in consumed rows, which
+    // needs a single sweep over the columns (L <= 128) and rows of >= 16 doubles
+    const bool fused_min = A.itemmin && A.LhPad <= 64 && 2 * RowGeom<N_>::RS >= 16;
+    if (fused_min) {
+        if constexpr (2 * RowGeom<N_>::RS >= 16)
+            return two ? launch_sq_elev2<N_, DIM, MODE, 2, true>(plan, A, st)
+                       : launch_sq_elev2<N_, DIM, MODE, 1, true>(plan, A, st);
+    }
+    int rc = two ? launch_sq_elev2<N_, DIM, MODE, 2, false>(plan, A, st)
+                 : launch_sq_elev2<N_, DIM, MODE, 1, false>(plan, A, st);
+    if (rc != BEZ_OK || !A.itemmin) return rc;
+    const long long rows = (long long)A.B * A.nitems;         // rare shapes: separate reduction pass
+    item_min_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(A.out, rows, A.L, A.itemmin);
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;
 }
@@ -305,16 +448,6 @@ int dispatch_degree(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) 
     return BEZ_EUNSUPPORTED;
 }
 
-int run_item_min(const SqElevArgs &A, cudaStream_t st) {
-    if (!A.itemmin) return BEZ_OK;
-    const long long rows = (long long)A.B * A.nitems;
-    const int threads = 256;
-    const long long blocks = (rows * 32 + threads - 1) / threads;
-    item_min_kernel<<<(unsigned)blocks, threads, 0, st>>>(A.out, rows, A.L, A.itemmin);
-    BEZ_CUDA(cudaGetLastError());
-    return BEZ_OK;
-}
-
 }  // namespace
 
 extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, int B, int N,
@@ -332,9 +465,7 @@ extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, i
     A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
     A.alpha = 1.0; A.beta = -maxSep2;
-    int rc = dispatch_degree<PAIR>(plan, A, (cudaStream_t)stream);
-    if (rc != BEZ_OK) return rc;
-    return run_item_min(A, (cudaStream_t)stream);
+    return dispatch_degree<PAIR>(plan, A, (cudaStream_t)stream);
 }
 
 extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, const double *d_tf,
@@ -382,7 +513,8 @@ extern "C" int bez_assemble_cpts(const bez_plan *plan, const double *d_x, int B,
     A.tf_fixed = tf_fixed; A.init = d_init; A.fin = d_final; A.ispeed = d_ispeed;
     A.fspeed = d_fspeed; A.icos = d_icos; A.isin = d_isin; A.fcos = d_fcos; A.fsin = d_fsin;
     A.obst = d_obst; A.cpts = d_cpts; A.tf = d_tf;
-    const long long total = (long long)B * plan->dim * (plan->n + 1) * (numVeh + nObs);
+    const int S = (plan->dim * (plan->n + 1) + 1) / 2 * 2;
+    const long long total = (long long)B * (numVeh + nObs) * S;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     assemble_cpts_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);

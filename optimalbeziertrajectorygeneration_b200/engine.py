@@ -97,6 +97,7 @@ class ConstraintEngine:
         obst = None if point_obstacles is None else np.asarray(point_obstacles, dtype=np.float64)
         self.nObs = 0 if obst is None else int(obst.shape[0])
         self.N = self.numVeh + self.nObs
+        self.row_stride = (self.dim * (self.n + 1) + 1) // 2 * 2
 
         def dev(a):
             return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
@@ -151,10 +152,10 @@ class ConstraintEngine:
     # -- A0 -----------------------------------------------------------------
     def assemble(self, d_x, elev=0):
         """reshapeVector (+ obstacle rows) for every row of d_x [B, nvar].
-        Returns (cpts [B, dim, n+1, N], tf [B])."""
+        Returns (cpts [B, N, S], tf [B]) with S = dim*(n+1) rounded up to even."""
         B = int(d_x.shape[0])
         plan = self.plan(elev)
-        cpts = torch.empty((B, self.dim, self.n + 1, self.N), dtype=F64, device=self.device)
+        cpts = torch.empty((B, self.N, self.row_stride), dtype=F64, device=self.device)
         tf = torch.empty((B,), dtype=F64, device=self.device)
         _capi.call("bez_assemble_cpts", plan.handle, _ptr(d_x), B, self.nvar, self.numVeh, self.nObs,
                    int(self.fixed_ends), int(self.dubins), int(self.timeopt), self.tf_fixed,
@@ -170,7 +171,7 @@ class ConstraintEngine:
         lexicographic pair list.  Returns out [B, npairs, L] (device)."""
         plan = self.plan(elev)
         B = int(cpts.shape[0])
-        N = int(cpts.shape[3]) if n_curves is None else int(n_curves)
+        N = int(cpts.shape[1]) if n_curves is None else int(n_curves)
         if npairs is None:
             npairs = num_pairs(N) - pair_begin
         if out is None:
@@ -183,7 +184,7 @@ class ConstraintEngine:
     def speed(self, cpts, tf, elev, alpha, beta, veh_begin=0, nveh=None, out=None):
         plan = self.plan(elev)
         B = int(cpts.shape[0])
-        N = int(cpts.shape[3])
+        N = int(cpts.shape[1])
         if nveh is None:
             nveh = self.numVeh - veh_begin
         if out is None:

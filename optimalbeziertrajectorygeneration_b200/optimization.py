@@ -196,8 +196,9 @@ class BezOptimization:
         (the same one every constraint closure uses) and copied back as the
         reference's [numVeh*dim, deg+1] matrix."""
         eng = self._engine(with_obstacles=False)
-        cpts, _ = eng.assemble(eng.upload(x), 0)             # [1, dim, n+1, numVeh]
-        y = eng.download(cpts.permute(0, 3, 1, 2).contiguous())
+        cpts, _ = eng.assemble(eng.upload(x), 0)             # [1, numVeh, S]
+        rows = self.model['dim'] * (self.model['deg'] + 1)
+        y = eng.download(cpts[0, :, :rows].contiguous())
         return y.reshape(self.model['numVeh'] * self.model['dim'], self.model['deg'] + 1)
 
     # ------------------------------------------------------------------
