@@ -108,6 +108,53 @@ int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, const double *
                       int B, int N, int veh_begin, int nveh,
                       double alpha, double beta, double *d_out, void *stream);
 
+/* ---- A6: _maxAngularRateConstraints -> _angularRateSqr (optimization.py:425-459,
+ * 578-611) with Bezier.mul / multiplyBezCurves (bezier.py:376-432, 1211-1246):
+ * 2-D vehicles only (the reference raises ValueError otherwise, optimization.py:590).
+ * Tables (host, scipy.special.binom, m = n + elev):
+ *   h_Tpos   [(n+1)*(m+1)]  elevMatrix(n, elev)
+ *   h_elev1m [m*(m+1)]      elevMatrix(m-1, 1)
+ *   h_Cm [m+1] = C(m,.)     h_C2m [2m+1] = C(2m,.)
+ *   d_out [B][nveh][4m+1] = alpha * (num^2/den^2) + beta   (max rate: alpha=-1, beta=maxAngRate^2)
+ *   row_stride = S of the control-point rows (see top of file)
+ */
+typedef struct bez_angrate_tables bez_angrate_tables;
+int bez_angrate_tables_create(int n, int elev, int device, const double *h_Tpos,
+                              const double *h_elev1m, const double *h_Cm, const double *h_C2m,
+                              bez_angrate_tables **out);
+int bez_angrate_tables_destroy(bez_angrate_tables *tables);
+int bez_angrate_sq(const bez_angrate_tables *tables, const double *d_cpts, const double *d_tf,
+                   int B, int N, int row_stride, int veh_begin, int nveh,
+                   double alpha, double beta, double *d_out, void *stream);
+
+/* ---- A7: the finite-difference Jacobian SciPy's SLSQP forms from nvar+1 calls
+ * of the constraint callables (scipy/optimize/_slsqp_py.py:349-367 ->
+ * _numdiff.py:585-596, 683-712):  J[:,k] = (f(x+h_k e_k) - f(x)) / dx_k,
+ * dx_k = (x_k+h_k) - x_k.  Both constraints are quadratic in the control points,
+ * which are affine in x, so the quotient is evaluated in closed form
+ *      J[:,k] = elev( scale * B(2a + dx_k*delta, delta) ),  delta = d a / d x_k
+ * (no cancellation; only rows that depend on x_k are touched).
+ *   d_cpts [N][S]   control points of the base x (bez_assemble_cpts with B = 1)
+ *   ncols, offset   free control points per row of x and index of the first one
+ *   d_dx   [nvar]   SciPy's divisors
+ *   d_dir  [N][S]   d(control points)/d x_kdir for a variable that moves every
+ *                   curve (tf of time-optimal problems), kdir = its index or -1
+ *   dense = 1: d_out is J^T [nvar][ld] (zero-filled here, ld >= rows of the block;
+ *              row k holds column k of J, so stores stay coalesced)
+ *   dense = 0: sweep layout, [numVeh*dim*ncols][N-1][L] (partner curves in
+ *              ascending order, the vehicle itself skipped) followed, when
+ *              kdir >= 0, by [P][L] for the kdir column.
+ */
+int bez_jac_sepsq_elev(const bez_plan *plan, const double *d_cpts, int N, int numVeh,
+                       int ncols, int offset, const double *d_dx, const double *d_dir,
+                       int kdir, int dense, double *d_out, int64_t ld, void *stream);
+/* speed rows: alpha as in bez_speed_sq_elev; sweep layout [numVeh*dim*ncols][L]
+ * (+ [numVeh][L] for kdir). */
+int bez_jac_speed_sq_elev(const bez_plan *plan, const double *d_cpts, int N, int numVeh,
+                          int ncols, int offset, double tf, double alpha,
+                          const double *d_dx, const double *d_dir, int kdir, int dense,
+                          double *d_out, int64_t ld, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

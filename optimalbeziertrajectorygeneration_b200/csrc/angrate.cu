@@ -1,0 +1,223 @@
+// Angular-rate constraint (A6 of SURVEY.md section 8) for sm_100a.
+//
+// Reference: _maxAngularRateConstraints / _angularRateSqr (optimization.py:425-459,
+// 578-611): per 2-D vehicle  pos.elev(E) -> x', x'', y', y'' (Bezier.diff keeps the
+// degree m = n+E) -> num = y''*x' - x''*y', den = x'*x' + y'*y' (degree 2m)
+// -> num*num / den*den control point by control point (degree 4m).
+//
+// One CTA per (evaluation point, vehicle); all curves live in shared memory.
+// Bernstein products are evaluated as plain convolutions of binomially
+// pre-scaled coefficients,  (a*b)_k = sum_i [C(m,i)a_i][C(m,k-i)b_{k-i}] / C(2m,k),
+// with the same scipy.special.binom values the reference's weight tables are
+// built from.  The degree-2m results are kept pre-scaled for the
+// squares, and the common 1/C(4m,k) of numerator and denominator cancels in the
+// ratio, so neither the 172 MB dense coefficient matrix of the reference
+// (bezier.py:1183-1208 at m = 110) nor C(4m,.) is ever formed.  The squares
+// (2 x (2m+1)^2 MACs) use a 4-output register tile with a sliding window so
+// that shared-memory traffic is one load per two DFMAs.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+struct bez_angrate_tables {
+    int n, elev, m, device;
+    double *d_Tpos;   // elevMatrix(n, E)           [n+1][m+1]
+    double *d_lo;     // elevMatrix(m-1,1)[k][k]     [m+1]
+    double *d_hi;     // elevMatrix(m-1,1)[k-1][k]   [m+1]
+    double *d_Cm;     // C(m, .)                     [m+1]
+    double *d_C2m;    // C(2m, .)                    [2m+1]
+};
+
+namespace {
+
+constexpr int kAThreads = 128;
+constexpr int kPad = 4;     // zero padding on both sides of the degree-2m rows
+
+struct AngArgs {
+    const double *cpts, *tf;
+    const double *Tpos, *lo, *hi, *Cm, *C2m;
+    double *out;
+    int B, N, S, n, m, veh_begin, nveh;
+    double alpha, beta;
+};
+
+__global__ void __launch_bounds__(kAThreads) angrate_kernel(const AngArgs A) {
+    extern __shared__ __align__(16) double sm[];
+    const int m = A.m, n = A.n, m1 = m + 1, L2 = 2 * m + 1;
+    double *px = sm, *py = px + m1;
+    double *xD = py + m1, *yD = xD + m1, *xDD = yD + m1, *yDD = xDD + m1;
+    double *tmpx = yDD + m1, *tmpy = tmpx + m1;
+    double *NUM = tmpy + m1 + kPad;                 // [-kPad, L2 + kPad)
+    double *DEN = NUM + L2 + 2 * kPad;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / A.nveh;
+    const int v = A.veh_begin + (blockIdx.x - b * A.nveh);
+    const double *row = A.cpts + ((size_t)b * A.N + v) * A.S;
+    const double val = (double)m / __ldg(A.tf + b);            // diffMatrix(m, tf): m/tf
+
+    // pos.elev(E)   (bezier.py:469-495)
+    for (int i = tid; i < m1; i += kAThreads) {
+        double sx = 0.0, sy = 0.0;
+        for (int j = 0; j <= n; ++j) {
+            const double t = __ldg(A.Tpos + (size_t)j * m1 + i);
+            sx = fma(__ldg(row + j), t, sx);
+            sy = fma(__ldg(row + n + 1 + j), t, sy);
+        }
+        px[i] = sx;
+        py[i] = sy;
+    }
+    for (int i = tid; i < 2 * kPad; i += kAThreads) {
+        const int off = (i < kPad) ? (i - kPad) : (L2 + i - kPad);
+        NUM[off] = 0.0;
+        DEN[off] = 0.0;
+    }
+    __syncthreads();
+    // first derivatives: np.dot(cpts, Dm) then .elev(1)   (bezier.py:497-519)
+    for (int k = tid; k < m; k += kAThreads) {
+        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
+        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
+    }
+    __syncthreads();
+    for (int k = tid; k < m1; k += kAThreads) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        xD[k] = qx;
+        yD[k] = qy;
+    }
+    __syncthreads();
+    for (int k = tid; k < m; k += kAThreads) {
+        tmpx[k] = xD[k] * (-val) + xD[k + 1] * val;
+        tmpy[k] = yD[k] * (-val) + yD[k + 1] * val;
+    }
+    __syncthreads();
+    for (int k = tid; k < m1; k += kAThreads) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k), c = __ldg(A.Cm + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        xDD[k] = qx * c;                      // pre-scale by C(m,k)
+        yDD[k] = qy * c;
+    }
+    __syncthreads();
+    for (int k = tid; k < m1; k += kAThreads) {
+        const double c = __ldg(A.Cm + k);
+        xD[k] *= c;
+        yD[k] *= c;
+    }
+    __syncthreads();
+    // degree-2m curves, kept pre-scaled by C(2m,k):
+    //   NUM = y''*x' - x''*y'      DEN = x'*x' + y'*y'      (optimization.py:603,605)
+    for (int k = tid; k < L2; k += kAThreads) {
+        const int ilo = k > m ? k - m : 0, ihi = k < m ? k : m;
+        double p1 = 0.0, p2 = 0.0, q1 = 0.0, q2 = 0.0;
+        for (int i = ilo; i <= ihi; ++i) {
+            const double x1 = xD[k - i], y1 = yD[k - i];
+            p1 = fma(yDD[i], x1, p1);
+            p2 = fma(xDD[i], y1, p2);
+            q1 = fma(xD[i], x1, q1);
+            q2 = fma(yD[i], y1, q2);
+        }
+        NUM[k] = p1 - p2;
+        DEN[k] = q1 + q2;
+    }
+    __syncthreads();
+    // squares (optimization.py:604,606) and the control-point-wise ratio (:608);
+    // 4 consecutive outputs per thread, sliding window over the second factor
+    const int L4 = 4 * m + 1;
+    double *out = A.out + ((size_t)b * A.nveh + (v - A.veh_begin)) * L4;
+    for (int k0 = 4 * tid; k0 < L4; k0 += 4 * kAThreads) {
+        const int ilo = k0 > 2 * m ? k0 - 2 * m : 0;
+        const int ihi = (k0 + 3) < 2 * m ? (k0 + 3) : 2 * m;
+        double nn[4] = {0, 0, 0, 0}, dd[4] = {0, 0, 0, 0};
+        double wn[4], wd[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { wn[r] = NUM[k0 + r - ilo]; wd[r] = DEN[k0 + r - ilo]; }
+        for (int i = ilo; i <= ihi; ++i) {
+            const double an = NUM[i], ad = DEN[i];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { nn[r] = fma(an, wn[r], nn[r]); dd[r] = fma(ad, wd[r], dd[r]); }
+            wn[3] = wn[2]; wn[2] = wn[1]; wn[1] = wn[0]; wn[0] = NUM[k0 - i - 1];
+            wd[3] = wd[2]; wd[2] = wd[1]; wd[1] = wd[0]; wd[0] = DEN[k0 - i - 1];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (k0 + r < L4) out[k0 + r] = fma(A.alpha, nn[r] / dd[r], A.beta);
+    }
+}
+
+}  // namespace
+
+extern "C" int bez_angrate_tables_create(int n, int elev, int device, const double *h_Tpos,
+                                         const double *h_elev1m, const double *h_Cm,
+                                         const double *h_C2m, bez_angrate_tables **out) {
+    BEZ_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    BEZ_REQUIRE(h_Tpos && h_elev1m && h_Cm && h_C2m, "tables are NULL");
+    BEZ_REQUIRE(n >= 1 && elev >= 0, "bad degree / elevation");
+    const int m = n + elev;
+    if (m > 250) {
+        bez_set_error("bez_angrate_tables_create: n+elev = %d > 250 (C(2m,m)^2 would overflow fp64)", m);
+        return BEZ_EUNSUPPORTED;
+    }
+    BEZ_CUDA(cudaSetDevice(device));
+    bez_angrate_tables *t = (bez_angrate_tables *)calloc(1, sizeof(bez_angrate_tables));
+    if (!t) { bez_set_error("out of host memory"); return BEZ_ENOMEM; }
+    t->n = n; t->elev = elev; t->m = m; t->device = device;
+    const int m1 = m + 1;
+    double *lo = (double *)malloc(sizeof(double) * m1), *hi = (double *)malloc(sizeof(double) * m1);
+    // elevMatrix(m-1,1) is [m][m+1]: q_k = E1[k-1][k] d_{k-1} + E1[k][k] d_k
+    for (int k = 0; k < m1; ++k) {
+        lo[k] = (k < m) ? h_elev1m[(size_t)k * m1 + k] : 0.0;
+        hi[k] = (k > 0) ? h_elev1m[(size_t)(k - 1) * m1 + k] : 0.0;
+    }
+    cudaError_t e = cudaSuccess;
+#define UP(dst, src, cnt)                                                                    \
+    if (e == cudaSuccess) e = cudaMalloc((void **)&(dst), sizeof(double) * (cnt));           \
+    if (e == cudaSuccess) e = cudaMemcpy((dst), (src), sizeof(double) * (cnt), cudaMemcpyHostToDevice);
+    UP(t->d_Tpos, h_Tpos, (size_t)(n + 1) * m1)
+    UP(t->d_lo, lo, m1)
+    UP(t->d_hi, hi, m1)
+    UP(t->d_Cm, h_Cm, m1)
+    UP(t->d_C2m, h_C2m, 2 * m + 1)
+#undef UP
+    free(lo);
+    free(hi);
+    if (e != cudaSuccess) {
+        cudaFree(t->d_Tpos); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_Cm); cudaFree(t->d_C2m);
+        free(t);
+        return bez_cuda_fail(e, "angular-rate table upload");
+    }
+    *out = t;
+    return BEZ_OK;
+}
+
+extern "C" int bez_angrate_tables_destroy(bez_angrate_tables *t) {
+    if (!t) return BEZ_OK;
+    cudaFree(t->d_Tpos); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_Cm); cudaFree(t->d_C2m);
+    free(t);
+    return BEZ_OK;
+}
+
+extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts, const double *d_tf,
+                              int B, int N, int row_stride, int veh_begin, int nveh,
+                              double alpha, double beta, double *d_out, void *stream) {
+    BEZ_REQUIRE(t && d_cpts && d_tf && d_out, "NULL argument");
+    BEZ_REQUIRE(B >= 0 && N >= 0 && veh_begin >= 0 && nveh >= 0 && veh_begin + nveh <= N,
+                "vehicle range outside [0, N)");
+    BEZ_REQUIRE(row_stride >= 2 * (t->n + 1), "control-point rows are not two dimensional");
+    if (B == 0 || nveh == 0) return BEZ_OK;
+    BEZ_CUDA(cudaSetDevice(t->device));
+    AngArgs A;
+    A.cpts = d_cpts; A.tf = d_tf; A.Tpos = t->d_Tpos; A.lo = t->d_lo; A.hi = t->d_hi;
+    A.Cm = t->d_Cm; A.C2m = t->d_C2m; A.out = d_out; A.B = B; A.N = N; A.S = row_stride;
+    A.n = t->n; A.m = t->m; A.veh_begin = veh_begin; A.nveh = nveh; A.alpha = alpha; A.beta = beta;
+    const size_t shmem = sizeof(double) * ((size_t)8 * (t->m + 1) + 2 * (2 * t->m + 1 + 2 * kPad) + kPad);
+    static size_t attr_set = 0;
+    if (shmem > 48 * 1024 && shmem > attr_set) {
+        BEZ_CUDA(cudaFuncSetAttribute(angrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        attr_set = shmem;
+    }
+    angrate_kernel<<<(unsigned)((long long)B * nveh), kAThreads, shmem, (cudaStream_t)stream>>>(A);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}

@@ -1,0 +1,335 @@
+// Finite-difference Jacobian columns of the separation and speed constraints
+// (A7 of SURVEY.md section 8) for sm_100a.
+//
+// SciPy's SLSQP forms  J[:,k] = (f(x + h_k e_k) - f(x)) / dx_k,  dx_k = (x_k+h_k) - x_k
+// with nvar+1 calls of the constraint callable (scipy/optimize/_slsqp_py.py:349-367,
+// _numdiff.py:585-596, 683-712).  Both constraints are quadratic forms of the control
+// points, which are affine in x (reshapeVector), so the quotient has the closed form
+//     J[:,k] = elev( scale * B(2a + dx*delta, delta) )
+// where a is the curve being squared (c_i - c_j, or the derivative curve), delta =
+// d a / d x_k and B is the Bernstein product.  Evaluating that directly is free of the
+// cancellation that limits the literal difference to ~1e-7 relative accuracy, costs the
+// same fused "square -> fold -> elevate" pipeline as one constraint row, and only
+// touches the rows that depend on x_k:
+//   J_PAIR_VAR   item = (variable kk of vehicle v, partner u != v)     N-1 rows per variable
+//   J_PAIR_DIR   item = pair p, for a variable that moves every curve (tf of time-optimal
+//                Dubins problems): delta = dir_i - dir_j, dir = d y / d tf
+//   J_SPEED_VAR  item = variable kk -> the speed row of its vehicle
+//   J_SPEED_DIR  item = vehicle v, tf variable (moves control points and the n/tf factor)
+// Output either in the sweep layout [item][L] or scattered into a dense J^T [nvar][ld]
+// (rows of J^T are contiguous, so stores stay coalesced; the host hands SciPy J^T.T).
+#include "sq_elev_core.cuh"
+
+namespace {
+using namespace bezcore;
+
+enum JMode { J_PAIR_VAR = 0, J_PAIR_DIR = 1, J_SPEED_VAR = 2, J_SPEED_DIR = 3 };
+
+template <int N_>
+struct FullWeights { double w[(N_ + 1) * (N_ + 1)]; };
+
+struct JacArgs {
+    const double *cpts;   // [N][S] base point
+    const double *dir;    // [N][S] d y / d x_kdir (DIR modes)
+    const double *dx;     // [nvar]
+    const double *PQ;     // folded elevation table
+    double *out;
+    long long nitems;
+    long long ld;         // dense: row length of J^T
+    int N, numVeh, L, Lh, LhPad;
+    int ncols, offset;    // free columns per row of x, first free control point
+    int kdir;             // variable index served by the DIR modes
+    int dense;
+    double tf;            // SPEED modes
+    double scale;         // alpha * dim / 2
+};
+
+template <int N_, int DIM, int JMODE>
+__global__ void __launch_bounds__(kThreads, 3)
+jac_sq_elev_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeights<N_> DW) {
+    constexpr int NC = N_ + 1;
+    constexpr int NT = 2 * N_ + 1;
+    constexpr int RS = RowGeom<N_>::RS;
+    constexpr int CPL = 2;
+    constexpr int S = (DIM * NC + 1) / 2 * 2;
+    constexpr bool DIRMODE = (JMODE == J_PAIR_DIR || JMODE == J_SPEED_DIR);
+    constexpr int ND = DIRMODE ? DIM : 1;
+    extern __shared__ __align__(16) double smem[];
+    // layout: [kWarps][32][RS] double2 rows | [NT][LhPad] table | [kWarps][32] row offsets
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2 *rows = reinterpret_cast<double2 *>(smem) + (size_t)warp * 32 * RS;
+    double *tab = smem + (size_t)kWarps * 32 * RS * 2;
+    long long *rowoff = reinterpret_cast<long long *>(tab + (size_t)NT * A.LhPad) + warp * 32;
+
+    for (int i = threadIdx.x; i < NT * A.LhPad; i += kThreads) tab[i] = __ldg(A.PQ + i);
+    __syncthreads();
+
+    const long long nwt = (A.nitems + 31) >> 5;
+    const long long gwarp = (long long)blockIdx.x * kWarps + warp;
+    const long long nwarps = (long long)gridDim.x * kWarps;
+    const int ngroups = (A.LhPad / 32 + CPL - 1) / CPL;
+    const int dim_ncols = DIM * A.ncols;
+
+    for (long long wt = gwarp; wt < nwt; wt += nwarps) {
+        const long long t0 = wt << 5;
+        const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
+        {
+            const long long item = t0 + (lane < cnt ? lane : cnt - 1);
+            double a[ND][NC], dl[ND][NC];
+            double dxk;
+            long long ro;
+            if (JMODE == J_PAIR_VAR) {
+                const long long kk = item / (A.N - 1);
+                const int uu = (int)(item - kk * (A.N - 1));
+                const int v = (int)(kk / dim_ncols);
+                const int rem = (int)(kk - (long long)v * dim_ncols);
+                const int d = rem / A.ncols;
+                const int c = A.offset + (rem - d * A.ncols);
+                const int u = uu + (uu >= v ? 1 : 0);
+                const int vi = v < u ? v : u, vj = v < u ? u : v;
+                const double sg = v < u ? 1.0 : -1.0;
+                const double *pi = A.cpts + (size_t)vi * S + d * NC;
+                const double *pj = A.cpts + (size_t)vj * S + d * NC;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    a[0][k] = __ldg(pi + k) - __ldg(pj + k);
+                    dl[0][k] = (k == c) ? sg : 0.0;
+                }
+                dxk = __ldg(A.dx + kk);
+                const long long p = bez_pair_row_offset(vi, A.N) + (vj - vi - 1);
+                ro = A.dense ? kk * A.ld + p * A.L : item * (long long)A.L;
+            } else if (JMODE == J_PAIR_DIR) {
+                int vi, vj;
+                bez_pair_decode(item, A.N, vi, vj);
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        a[d][k] = __ldg(A.cpts + (size_t)vi * S + d * NC + k) -
+                                  __ldg(A.cpts + (size_t)vj * S + d * NC + k);
+                        dl[d][k] = __ldg(A.dir + (size_t)vi * S + d * NC + k) -
+                                   __ldg(A.dir + (size_t)vj * S + d * NC + k);
+                    }
+                dxk = __ldg(A.dx + A.kdir);
+                ro = A.dense ? (long long)A.kdir * A.ld + item * A.L : item * (long long)A.L;
+            } else if (JMODE == J_SPEED_VAR) {
+                const long long kk = item;
+                const int v = (int)(kk / dim_ncols);
+                const int rem = (int)(kk - (long long)v * dim_ncols);
+                const int d = rem / A.ncols;
+                const int c = A.offset + (rem - d * A.ncols);
+                const double val = (double)N_ / A.tf;
+                const double *pv = A.cpts + (size_t)v * S + d * NC;
+                double pt[NC], dd[NC], de[NC];
+#pragma unroll
+                for (int k = 0; k < NC; ++k) pt[k] = __ldg(pv + k);
+#pragma unroll
+                for (int k = 0; k < N_; ++k) {
+                    dd[k] = pt[k] * (-val) + pt[k + 1] * val;
+                    de[k] = ((k == c) ? -val : 0.0) + ((k + 1 == c) ? val : 0.0);
+                }
+                dd[N_] = 0.0; de[N_] = 0.0;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    double q = dd[k] * DW.lo[k], r = de[k] * DW.lo[k];
+                    if (k > 0) { q = dd[k - 1] * DW.hi[k] + q; r = de[k - 1] * DW.hi[k] + r; }
+                    a[0][k] = q;
+                    dl[0][k] = r;
+                }
+                dxk = __ldg(A.dx + kk);
+                ro = A.dense ? kk * A.ld + (long long)v * A.L : item * (long long)A.L;
+            } else {   // J_SPEED_DIR: tf moves the control points (dir) and the n/tf factor
+                const int v = (int)item;
+                dxk = __ldg(A.dx + A.kdir);
+                const double val = (double)N_ / A.tf;
+                const double valp = (double)N_ / (A.tf + dxk);
+                const double gam = -(double)N_ / (A.tf * (A.tf + dxk));     // (valp - val) / dx
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    double pt[NC], pd[NC], dd[NC], de[NC];
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        pt[k] = __ldg(A.cpts + (size_t)v * S + d * NC + k);
+                        pd[k] = __ldg(A.dir + (size_t)v * S + d * NC + k);
+                    }
+#pragma unroll
+                    for (int k = 0; k < N_; ++k) {
+                        dd[k] = pt[k] * (-val) + pt[k + 1] * val;
+                        de[k] = valp * (pd[k + 1] - pd[k]) + gam * (pt[k + 1] - pt[k]);
+                    }
+                    dd[N_] = 0.0; de[N_] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        double q = dd[k] * DW.lo[k], r = de[k] * DW.lo[k];
+                        if (k > 0) { q = dd[k - 1] * DW.hi[k] + q; r = de[k - 1] * DW.hi[k] + r; }
+                        a[d][k] = q;
+                        dl[d][k] = r;
+                    }
+                }
+                ro = A.dense ? (long long)A.kdir * A.ld + (long long)v * A.L : item * (long long)A.L;
+            }
+            rowoff[lane] = ro;
+
+            // s = B(2a + dx*delta, delta)   (Bernstein product, full weight matrix)
+            double s[2 * N_ + 1];
+#pragma unroll
+            for (int k = 0; k <= 2 * N_; ++k) s[k] = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double uvec[NC];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) uvec[i] = fma(dxk, dl[d][i], 2.0 * a[d][i]);
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+#pragma unroll
+                    for (int j = 0; j < NC; ++j)
+                        s[i + j] = fma(FW.w[i * NC + j], uvec[i] * dl[d][j], s[i + j]);
+            }
+            double2 *row = rows + (size_t)lane * RS;
+#pragma unroll
+            for (int j = 0; j < N_; ++j) {
+                const double lo = s[j] * A.scale, hi = s[2 * N_ - j] * A.scale;
+                row[j] = make_double2(lo + hi, lo - hi);
+            }
+            row[N_] = make_double2(s[N_] * A.scale, 0.0);
+        }
+        __syncwarp();
+        for (int g = 0; g < ngroups; ++g) {
+            if (cnt == 32)
+                sweep_columns<N_, CPL, false, true, true>(rows, tab, A.out, g, lane, 32, A.L, A.Lh, A.LhPad, 0.0, rowoff);
+            else
+                sweep_columns<N_, CPL, false, false, true>(rows, tab, A.out, g, lane, cnt, A.L, A.Lh, A.LhPad, 0.0, rowoff);
+        }
+        __syncwarp();
+    }
+}
+
+template <int N_, int DIM, int JMODE>
+int launch_jac(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
+    FullWeights<N_> FW;
+    DiffWeights<N_> DW;
+    for (int i = 0; i < (N_ + 1) * (N_ + 1); ++i) FW.w[i] = plan->h_W[i];
+    for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
+    const size_t shmem = ((size_t)kWarps * 32 * RowGeom<N_>::RS * 2 + (size_t)(2 * N_ + 1) * A.LhPad) * sizeof(double) +
+                         (size_t)kWarps * 32 * sizeof(long long);
+    if (shmem > 227 * 1024) {
+        bez_set_error("degree %d with elevation %d needs %zu bytes of shared memory (> 227 KB)",
+                      plan->n, plan->elev, shmem);
+        return BEZ_EUNSUPPORTED;
+    }
+    auto kern = jac_sq_elev_kernel<N_, DIM, JMODE>;
+    static size_t attr_set = 0;
+    if (shmem > attr_set) {
+        BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        attr_set = shmem;
+    }
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
+    if (per_sm < 1) per_sm = 1;
+    const long long nwt = (A.nitems + 31) / 32;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (nwt + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) return BEZ_OK;
+    kern<<<(unsigned)grid, kThreads, shmem, st>>>(A, FW, DW);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
+
+template <int N_, int JMODE>
+int jdispatch_dim(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
+    switch (plan->dim) {
+        case 1: return launch_jac<N_, 1, JMODE>(plan, A, st);
+        case 2: return launch_jac<N_, 2, JMODE>(plan, A, st);
+        case 3: return launch_jac<N_, 3, JMODE>(plan, A, st);
+    }
+    return BEZ_EUNSUPPORTED;
+}
+
+template <int JMODE>
+int jdispatch(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
+    switch (plan->n) {
+#define CASE(n_) case n_: return jdispatch_dim<n_, JMODE>(plan, A, st);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+        CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+    }
+    bez_set_error("degree %d has no Jacobian kernel instantiation (1..12 supported)", plan->n);
+    return BEZ_EUNSUPPORTED;
+}
+
+int fill_common(const bez_plan *plan, JacArgs &A, const double *d_cpts, const double *d_dir,
+                const double *d_dx, int N, int numVeh, int ncols, int offset, int kdir, int dense,
+                double *d_out, int64_t ld) {
+    A.cpts = d_cpts; A.dir = d_dir; A.dx = d_dx; A.PQ = plan->d_PQ; A.out = d_out;
+    A.ld = ld; A.N = N; A.numVeh = numVeh; A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
+    A.ncols = ncols; A.offset = offset; A.kdir = kdir; A.dense = dense; A.tf = 1.0; A.scale = 1.0;
+    return BEZ_OK;
+}
+
+}  // namespace
+
+extern "C" int bez_jac_sepsq_elev(const bez_plan *plan, const double *d_cpts, int N, int numVeh,
+                                  int ncols, int offset, const double *d_dx, const double *d_dir,
+                                  int kdir, int dense, double *d_out, int64_t ld, void *stream) {
+    BEZ_REQUIRE(plan && d_cpts && d_dx && d_out, "NULL argument");
+    BEZ_REQUIRE(N >= 2 && numVeh >= 1 && numVeh <= N && ncols >= 0 && offset >= 0, "bad sizes");
+    BEZ_REQUIRE(kdir < 0 || d_dir, "direction rows are NULL");
+    const long long P = (long long)N * (N - 1) / 2;
+    const long long nvarN = (long long)numVeh * plan->dim * ncols;
+    BEZ_REQUIRE(!dense || ld >= P * plan->L, "ld smaller than the constraint block");
+    BEZ_CUDA(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    JacArgs A;
+    fill_common(plan, A, d_cpts, d_dir, d_dx, N, numVeh, ncols, offset, kdir, dense, d_out, ld);
+    A.scale = 0.5 * plan->dim;
+    if (dense) {
+        const long long nvar = nvarN + (kdir >= 0 ? 1 : 0);
+        BEZ_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)nvar * (size_t)ld, st));
+    }
+    A.nitems = nvarN * (N - 1);
+    if (A.nitems > 0) {
+        int rc = jdispatch<J_PAIR_VAR>(plan, A, st);
+        if (rc != BEZ_OK) return rc;
+    }
+    if (kdir >= 0) {
+        if (!dense) A.out = d_out + (size_t)A.nitems * plan->L;
+        A.nitems = P;
+        return jdispatch<J_PAIR_DIR>(plan, A, st);
+    }
+    return BEZ_OK;
+}
+
+extern "C" int bez_jac_speed_sq_elev(const bez_plan *plan, const double *d_cpts, int N, int numVeh,
+                                     int ncols, int offset, double tf, double alpha,
+                                     const double *d_dx, const double *d_dir, int kdir, int dense,
+                                     double *d_out, int64_t ld, void *stream) {
+    BEZ_REQUIRE(plan && d_cpts && d_dx && d_out, "NULL argument");
+    BEZ_REQUIRE(N >= 1 && numVeh >= 1 && numVeh <= N && ncols >= 0 && offset >= 0, "bad sizes");
+    BEZ_REQUIRE(kdir < 0 || d_dir, "direction rows are NULL");
+    const long long nvarN = (long long)numVeh * plan->dim * ncols;
+    BEZ_REQUIRE(!dense || ld >= (long long)numVeh * plan->L, "ld smaller than the constraint block");
+    BEZ_CUDA(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    JacArgs A;
+    fill_common(plan, A, d_cpts, d_dir, d_dx, N, numVeh, ncols, offset, kdir, dense, d_out, ld);
+    A.scale = alpha * 0.5 * plan->dim;
+    A.tf = tf;
+    if (dense) {
+        const long long nvar = nvarN + (kdir >= 0 ? 1 : 0);
+        BEZ_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)nvar * (size_t)ld, st));
+    }
+    A.nitems = nvarN;
+    if (A.nitems > 0) {
+        int rc = jdispatch<J_SPEED_VAR>(plan, A, st);
+        if (rc != BEZ_OK) return rc;
+    }
+    if (kdir >= 0) {
+        if (!dense) A.out = d_out + (size_t)A.nitems * plan->L;
+        A.nitems = numVeh;
+        return jdispatch<J_SPEED_DIR>(plan, A, st);
+    }
+    return BEZ_OK;
+}

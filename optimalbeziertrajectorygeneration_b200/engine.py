@@ -68,6 +68,45 @@ class Plan:
             self.handle = None
 
 
+class AngRateTables:
+    """Device tables of the angular-rate kernel for one (degree, DEG_ELEV):
+    elevMatrix(n,E), elevMatrix(m-1,1), C(m,.), C(2m,.) with m = n+E, all from
+    scipy.special.binom like the reference's (bezier.py:1127-1147, 1183-1208)."""
+
+    _cache = {}
+
+    def __init__(self, n, elev, device):
+        from scipy.special import binom
+        _require_cuda()
+        self.n, self.elev, self.m, self.device = int(n), int(elev), int(n + elev), int(device)
+        m = self.m
+        Tpos = np.ascontiguousarray(_tables.elev_matrix(self.n, self.elev))
+        E1 = np.ascontiguousarray(_tables.elev_matrix(m - 1, 1))
+        Cm = np.ascontiguousarray(binom(m, np.arange(m + 1)), dtype=np.float64)
+        C2m = np.ascontiguousarray(binom(2 * m, np.arange(2 * m + 1)), dtype=np.float64)
+        handle = ctypes.c_void_p(0)
+        _capi.call("bez_angrate_tables_create", self.n, self.elev, self.device, Tpos.ctypes.data,
+                   E1.ctypes.data, Cm.ctypes.data, C2m.ctypes.data, ctypes.byref(handle))
+        self.handle = handle
+
+    @classmethod
+    def get(cls, n, elev, device):
+        key = (int(n), int(elev), int(device))
+        t = cls._cache.get(key)
+        if t is None:
+            t = cls._cache[key] = cls(*key)
+        return t
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                _capi.lib.bez_angrate_tables_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
 def num_pairs(N):
     return N * (N - 1) // 2
 
@@ -191,4 +230,98 @@ class ConstraintEngine:
             out = torch.empty((B, nveh, plan.L), dtype=F64, device=self.device)
         _capi.call("bez_speed_sq_elev", plan.handle, _ptr(cpts), _ptr(tf), B, N, int(veh_begin),
                    int(nveh), float(alpha), float(beta), _ptr(out), _stream())
+        return out
+
+    # -- A6 -------------------------------------------------------------------
+    def angrate(self, cpts, tf, elev, alpha, beta, veh_begin=0, nveh=None, out=None):
+        """alpha * (squared angular rate control points) + beta, [B, nveh, 4(n+E)+1]."""
+        if self.dim != 2:
+            raise ValueError('The input curve must be two dimensional,\n'
+                             'instead it is {} dimensional'.format(self.dim))
+        tabs = AngRateTables.get(self.n, elev, self.dev_index)
+        B, N = int(cpts.shape[0]), int(cpts.shape[1])
+        if nveh is None:
+            nveh = self.numVeh - veh_begin
+        L4 = 4 * (self.n + int(elev)) + 1
+        if out is None:
+            out = torch.empty((B, nveh, L4), dtype=F64, device=self.device)
+        _capi.call("bez_angrate_sq", tabs.handle, _ptr(cpts), _ptr(tf), B, N, self.row_stride,
+                   int(veh_begin), int(nveh), float(alpha), float(beta), _ptr(out), _stream())
+        return out
+
+    # -- A7 ---------------------------------------------------------------------
+    @staticmethod
+    def fd_steps(x0, abs_step=1.4901161193847656e-08):
+        """h and dx = (x0+h)-x0 exactly as SciPy's approx_derivative chooses them
+        for SLSQP (scipy/optimize/_numdiff.py:585-596; abs_step = sqrt(eps) from
+        _slsqp_py.py).  Host logic."""
+        x0 = np.asarray(x0, dtype=np.float64)
+        h = np.full_like(x0, abs_step)
+        dx = (x0 + h) - x0
+        sign = (x0 >= 0).astype(np.float64) * 2 - 1
+        h = np.where(dx == 0, np.finfo(np.float64).eps ** 0.5 * sign * np.maximum(1.0, np.abs(x0)), h)
+        return h, (x0 + h) - x0
+
+    def _direction_rows(self):
+        """d(control points)/d tf for time-optimal Dubins models: only control
+        points 1 and n-1 depend on tf (optimization.py:273-281)."""
+        if not (self.timeopt and self.dubins):
+            return None
+        if getattr(self, "_dir", None) is None:
+            D = torch.zeros((self.N, self.row_stride), dtype=F64, device=self.device)
+            nc = self.n + 1
+            cs_i = (self.d_icos, self.d_isin)
+            cs_f = (self.d_fcos, self.d_fsin)
+            for d in range(2):
+                D[:self.numVeh, d * nc + 1] += self.d_ispeed * cs_i[d] / self.n
+                D[:self.numVeh, d * nc + self.n - 1] -= self.d_fspeed * cs_f[d] / self.n
+            self._dir = D
+        return self._dir
+
+    def jac_separation(self, x, elev, dense=True):
+        """FD Jacobian of the separation block at x (host vector).
+        dense: returns J^T as a device tensor [nvar, P*L]; else the sweep layout."""
+        plan = self.plan(elev)
+        x = np.asarray(x, dtype=np.float64)
+        _, dx = self.fd_steps(x)
+        d_dx = torch.as_tensor(dx, device=self.device)
+        cpts, _ = self.assemble(self.upload(x), elev)
+        dirs = self._direction_rows()
+        kdir = self.nvar - 1 if dirs is not None else -1
+        P, L = num_pairs(self.N), plan.L
+        nvarN = self.numVeh * self.dim * self.ncols
+        if dense:
+            out = torch.empty((self.nvar, P * L), dtype=F64, device=self.device)
+            if self.timeopt and dirs is None:
+                out[self.nvar - 1].zero_()          # tf does not move any control point
+            ld = P * L
+        else:
+            out = torch.empty((nvarN * (self.N - 1) + (P if kdir >= 0 else 0), L), dtype=F64, device=self.device)
+            ld = 0
+        _capi.call("bez_jac_sepsq_elev", plan.handle, _ptr(cpts), self.N, self.numVeh, self.ncols,
+                   self.offset, _ptr(d_dx), _ptr(dirs), kdir, int(dense), _ptr(out), ld, _stream())
+        return out
+
+    def jac_speed(self, x, elev, alpha, dense=True):
+        plan = self.plan(elev)
+        x = np.asarray(x, dtype=np.float64)
+        _, dx = self.fd_steps(x)
+        d_dx = torch.as_tensor(dx, device=self.device)
+        cpts, _ = self.assemble(self.upload(x), elev)
+        tf = float(x[-1]) if self.timeopt else self.tf_fixed
+        dirs = self._direction_rows()
+        if self.timeopt and dirs is None:
+            dirs = torch.zeros((self.N, self.row_stride), dtype=F64, device=self.device)
+        kdir = self.nvar - 1 if self.timeopt else -1
+        L = plan.L
+        nvarN = self.numVeh * self.dim * self.ncols
+        if dense:
+            out = torch.empty((self.nvar, self.numVeh * L), dtype=F64, device=self.device)
+            ld = self.numVeh * L
+        else:
+            out = torch.empty((nvarN + (self.numVeh if kdir >= 0 else 0), L), dtype=F64, device=self.device)
+            ld = 0
+        _capi.call("bez_jac_speed_sq_elev", plan.handle, _ptr(cpts), self.N, self.numVeh, self.ncols,
+                   self.offset, tf, float(alpha), _ptr(d_dx), _ptr(dirs), kdir, int(dense), _ptr(out),
+                   ld, _stream())
         return out

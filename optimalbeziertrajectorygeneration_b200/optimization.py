@@ -149,6 +149,51 @@ class BezOptimization:
             return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
         return wrapper
 
+    @property
+    def maxAngularRateConstraints(self):
+        """optimization.py:171-187 -> _maxAngularRateConstraints (:425-459)."""
+        def wrapper(x):
+            if self.model['dim'] != 2:                      # optimization.py:590-593
+                msg = ('The input curve must be two dimensional,\n'
+                       'instead it is {} dimensional'.format(self.model['dim']))
+                raise ValueError(msg)
+            eng = self._engine(with_obstacles=False)
+            E = _deg_elev()
+            cpts, tf = eng.assemble(eng.upload(x), E)
+            out = eng.angrate(cpts, tf, E, -1.0, float(self.model['maxAngRate']) ** 2)
+            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+        return wrapper
+
+    # ------------------------------------------------------------------
+    # additive: Jacobians of the closures above, J[m, nvar], equal to what SLSQP
+    # would form by nvar+1 calls (SciPy's '2-point' rule and step), computed in one
+    # batched launch.  Hand them to SciPy as {'type': 'ineq', 'fun': f, 'jac': f_jac}.
+    @property
+    def temporalSeparationConstraints_jac(self):
+        def wrapper(x):
+            eng = self._engine(with_obstacles=True)
+            if eng.N <= 1:
+                return None
+            JT = eng.jac_separation(x, _deg_elev(), dense=True)
+            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+        return wrapper
+
+    @property
+    def maxSpeedConstraints_jac(self):
+        def wrapper(x):
+            eng = self._engine(with_obstacles=False)
+            JT = eng.jac_speed(x, _deg_elev(), -1.0, dense=True)
+            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+        return wrapper
+
+    @property
+    def minSpeedConstraints_jac(self):
+        def wrapper(x):
+            eng = self._engine(with_obstacles=False)
+            JT = eng.jac_speed(x, _deg_elev(), 1.0, dense=True)
+            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+        return wrapper
+
     # ------------------------------------------------------------------
     def generateGuess(self, std=0, seed=None):
         """optimization.py:189-240 (host logic; uses numpy's global RNG like

@@ -19,8 +19,29 @@ All functions accept a ``dtype`` so the same code can run in ``np.longdouble``
 to produce an (almost) exactly rounded finite-difference quotient, which is
 what Jacobian parity is judged against (hard part 1).
 """
+from fractions import Fraction
+
 import numpy as np
 from scipy.special import binom
+
+
+def _cast(a, dtype):
+    """array -> dtype; dtype=object means exact rationals (fractions.Fraction of
+    the fp64 values), used for the exactly rounded finite-difference quotient."""
+    a = np.asarray(a)
+    if dtype is object:
+        if a.dtype == object:
+            return a
+        out = np.empty(a.shape, dtype=object)
+        flat = out.reshape(-1)
+        for i, v in enumerate(a.reshape(-1)):
+            flat[i] = Fraction(float(v))
+        return out
+    return a.astype(dtype)
+
+
+def _num(v, dtype):
+    return Fraction(v) if dtype is object else dtype(v)
 
 # --------------------------------------------------------------------------
 # constant tables (bezier.py:1127-1147, 1151-1176, 1183-1208)
@@ -62,9 +83,9 @@ def prod_weights(m, n=None):
 
 def elev(cpts, R, dtype=np.float64):
     """Bezier.elev, bezier.py:469-495 (np.dot(cpts_row, elevMat))."""
-    cpts = np.atleast_2d(np.asarray(cpts, dtype=dtype))
+    cpts = np.atleast_2d(_cast(cpts, dtype))
     N = cpts.shape[1] - 1
-    T = elev_matrix(N, R).astype(dtype)
+    T = _cast(elev_matrix(N, R), dtype)
     out = np.zeros((cpts.shape[0], N + R + 1), dtype=dtype)
     for j in range(N + 1):          # ascending-j accumulation
         out += cpts[:, j:j + 1] * T[j:j + 1, :]
@@ -75,10 +96,10 @@ def mul(a, b, dtype=np.float64):
     """Bezier.mul / multiplyBezCurves for 1-D rows (bezier.py:376-432,
     1211-1246).  General (correct) product; the reference is only right for
     equal degrees (Q2), which is all the hot path uses."""
-    a = np.asarray(a, dtype=dtype).ravel()
-    b = np.asarray(b, dtype=dtype).ravel()
+    a = _cast(a, dtype).ravel()
+    b = _cast(b, dtype).ravel()
     m, n = a.size - 1, b.size - 1
-    W = prod_weights(m, n).astype(dtype)
+    W = _cast(prod_weights(m, n), dtype)
     out = np.zeros(m + n + 1, dtype=dtype)
     for i in range(m + 1):
         for j in range(n + 1):
@@ -91,10 +112,10 @@ def norm_square(cpts, dtype=np.float64):
 
     Returns the 2n+1 Bernstein coefficients of (dim/2) * sum_d c_d(t)^2 (Q1).
     """
-    cpts = np.atleast_2d(np.asarray(cpts, dtype=dtype))
+    cpts = np.atleast_2d(_cast(cpts, dtype))
     dim, n1 = cpts.shape
     n = n1 - 1
-    W = prod_weights(n).astype(dtype)
+    W = _cast(prod_weights(n), dtype)
     G = np.zeros((n1, n1), dtype=dtype)           # x.T @ x  (bezier.py:1746)
     for d in range(dim):
         G += np.outer(cpts[d], cpts[d])
@@ -103,15 +124,15 @@ def norm_square(cpts, dtype=np.float64):
         for j in range(n1):
             out[i + j] += W[i, j] * G[i, j]
     # S sums `dim` identical rows, then /2  (bezier.py:1750-1756, 884)
-    return (out * dtype(dim)) / dtype(2)
+    return (out * _num(dim, dtype)) / _num(2, dtype)
 
 
 def diff(cpts, T, dtype=np.float64):
     """Bezier.diff (bezier.py:497-519, 1100-1123): derivative control points
     n/T * (P[i+1]-P[i]) followed by one degree elevation (same degree n)."""
-    cpts = np.atleast_2d(np.asarray(cpts, dtype=dtype))
+    cpts = np.atleast_2d(_cast(cpts, dtype))
     n = cpts.shape[1] - 1
-    val = dtype(n) / dtype(T)
+    val = _num(n, dtype) / _num(T, dtype)
     # np.dot(cpts, Dm): column i = -val*P[i] + val*P[i+1]
     d = cpts[:, :-1] * (-val) + cpts[:, 1:] * val
     return elev(d, 1, dtype=dtype)
@@ -137,7 +158,7 @@ def de_casteljau_split(c, t, dtype=np.float64):
 
 def split(cpts, tDiv, t0=0.0, tf=1.0, dtype=np.float64):
     """Bezier.split (bezier.py:533-572)."""
-    cpts = np.atleast_2d(np.asarray(cpts, dtype=dtype))
+    cpts = np.atleast_2d(_cast(cpts, dtype))
     if np.isnan(tDiv):
         tDiv = 0
     t = (dtype(tDiv) - dtype(t0)) / (dtype(tf) - dtype(t0))
@@ -233,9 +254,9 @@ class Model:
 
 def reshape_vector(model, x, dtype=np.float64):
     """BezOptimization.reshapeVector (optimization.py:242-285)."""
-    x = np.asarray(x, dtype=dtype)
+    x = _cast(x, dtype)
     dim, deg, numVeh = model.dim, model.deg, model.numVeh
-    tf = dtype(model.tf)
+    tf = _num(model.tf, dtype)
     if model.timeopt:
         tf = x[-1]
         x = x[:-1]
@@ -244,18 +265,19 @@ def reshape_vector(model, x, dtype=np.float64):
     if model.has_pts:
         offset += 1
         for i in range(model.initPoints.shape[0]):
-            y[i * dim:(i + 1) * dim, 0] = model.initPoints[i]
-            y[i * dim:(i + 1) * dim, -1] = model.finalPoints[i]
+            y[i * dim:(i + 1) * dim, 0] = _cast(model.initPoints[i], dtype)
+            y[i * dim:(i + 1) * dim, -1] = _cast(model.finalPoints[i], dtype)
     if model.has_spd:
         offset += 1
-        initMag = model.initSpeeds.astype(dtype) * tf / deg
-        finalMag = model.finalSpeeds.astype(dtype) * tf / deg
+        initMag = _cast(model.initSpeeds.astype(np.float64), dtype) * tf / deg
+        finalMag = _cast(model.finalSpeeds.astype(np.float64), dtype) * tf / deg
         ia = model.initAngs.astype(np.float64)
         fa = model.finalAngs.astype(np.float64)
-        y[::2, 1] = model.initPoints[:, 0] + initMag * np.cos(ia).astype(dtype)
-        y[1::2, 1] = model.initPoints[:, 1] + initMag * np.sin(ia).astype(dtype)
-        y[::2, -2] = model.finalPoints[:, 0] - finalMag * np.cos(fa).astype(dtype)
-        y[1::2, -2] = model.finalPoints[:, 1] - finalMag * np.sin(fa).astype(dtype)
+        ip, fp = _cast(model.initPoints, dtype), _cast(model.finalPoints, dtype)
+        y[::2, 1] = ip[:, 0] + initMag * _cast(np.cos(ia), dtype)
+        y[1::2, 1] = ip[:, 1] + initMag * _cast(np.sin(ia), dtype)
+        y[::2, -2] = fp[:, 0] - finalMag * _cast(np.cos(fa), dtype)
+        y[1::2, -2] = fp[:, 1] - finalMag * _cast(np.sin(fa), dtype)
     y[:, offset:deg + 1 - offset] = x.reshape((dim * numVeh, model.numCols))
     return y
 
@@ -273,7 +295,7 @@ def stack_obstacles(model, y, dtype=np.float64):
     for obstacle in model.pointObstacles:
         for d in range(model.dim):
             rows.append([obstacle[d]] * (model.deg + 1))
-    return np.vstack((y, np.asarray(rows, dtype=dtype))), model.numVeh + len(model.pointObstacles)
+    return np.vstack((y, _cast(np.asarray(rows, dtype=np.float64), dtype))), model.numVeh + len(model.pointObstacles)
 
 
 def temporal_separation(y, nVeh, dim, maxSep, elev_R, dtype=np.float64):
@@ -281,19 +303,19 @@ def temporal_separation(y, nVeh, dim, maxSep, elev_R, dtype=np.float64):
     pair i<j (lexicographic) elev(normSquare(c_i - c_j), E) - maxSep^2."""
     if nVeh <= 1:
         return None
-    y = np.asarray(y, dtype=dtype)
+    y = _cast(y, dtype)
     out = []
     for i in range(nVeh - 1):
         for j in range(i + 1, nVeh):
             dv = y[i * dim:(i + 1) * dim] - y[j * dim:(j + 1) * dim]
             out.append(elev(norm_square(dv, dtype=dtype), elev_R, dtype=dtype)[0])
-    return np.concatenate(out) - dtype(maxSep) ** 2
+    return np.concatenate(out) - _num(maxSep, dtype) ** 2
 
 
 def speed_sq(y, nVeh, dim, tf, elev_R, dtype=np.float64):
     """Shared body of _min/_maxSpeedConstraints (optimization.py:373-382,
     411-420): elev(normSquare(diff(c_i)), E) for every vehicle."""
-    y = np.asarray(y, dtype=dtype)
+    y = _cast(y, dtype)
     out = []
     for i in range(nVeh):
         v = diff(y[i * dim:(i + 1) * dim], tf, dtype=dtype)
@@ -303,18 +325,18 @@ def speed_sq(y, nVeh, dim, tf, elev_R, dtype=np.float64):
 
 def max_speed(y, nVeh, dim, tf, maxSpeed, elev_R, dtype=np.float64):
     """_maxSpeedConstraints (optimization.py:387-422)."""
-    return dtype(maxSpeed) ** 2 - speed_sq(y, nVeh, dim, tf, elev_R, dtype)
+    return _num(maxSpeed, dtype) ** 2 - speed_sq(y, nVeh, dim, tf, elev_R, dtype)
 
 
 def min_speed(y, nVeh, dim, tf, minSpeed, elev_R, dtype=np.float64):
     """_minSpeedConstraints (optimization.py:349-384)."""
-    return speed_sq(y, nVeh, dim, tf, elev_R, dtype) - dtype(minSpeed) ** 2
+    return speed_sq(y, nVeh, dim, tf, elev_R, dtype) - _num(minSpeed, dtype) ** 2
 
 
 def angular_rate_sq(cpts2d, tf, dtype=np.float64):
     """_angularRateSqr (optimization.py:578-611) on a 2-D curve of degree m:
     control-point-wise ratio of two degree-4m Bernstein polynomials (Q11)."""
-    cpts2d = np.asarray(cpts2d, dtype=dtype)
+    cpts2d = _cast(cpts2d, dtype)
     if cpts2d.shape[0] != 2:
         raise ValueError('The input curve must be two dimensional,\n'
                          'instead it is {} dimensional'.format(cpts2d.shape[0]))
@@ -331,12 +353,12 @@ def angular_rate_sq(cpts2d, tf, dtype=np.float64):
 
 def max_angular_rate(y, nVeh, dim, tf, maxAngRate, elev_R, dtype=np.float64):
     """_maxAngularRateConstraints (optimization.py:425-459)."""
-    y = np.asarray(y, dtype=dtype)
+    y = _cast(y, dtype)
     out = []
     for i in range(nVeh):
         pos = elev(y[i * dim:(i + 1) * dim], elev_R, dtype=dtype)
         out.append(angular_rate_sq(pos, tf, dtype=dtype))
-    return dtype(maxAngRate) ** 2 - np.concatenate(out)
+    return _num(maxAngRate, dtype) ** 2 - np.concatenate(out)
 
 
 # closures with the reference's signatures -----------------------------------
@@ -353,15 +375,15 @@ def make_callables(model, elev_R, dtype=np.float64):
 
     def maxspd(x):
         return max_speed(reshape_vector(model, x, dtype), model.numVeh, model.dim,
-                         model_tf(model, np.asarray(x, dtype=dtype)), model.maxSpeed, elev_R, dtype)
+                         model_tf(model, _cast(x, dtype)), model.maxSpeed, elev_R, dtype)
 
     def minspd(x):
         return min_speed(reshape_vector(model, x, dtype), model.numVeh, model.dim,
-                         model_tf(model, np.asarray(x, dtype=dtype)), model.minSpeed, elev_R, dtype)
+                         model_tf(model, _cast(x, dtype)), model.minSpeed, elev_R, dtype)
 
     def angrate(x):
         return max_angular_rate(reshape_vector(model, x, dtype), model.numVeh, model.dim,
-                                model_tf(model, np.asarray(x, dtype=dtype)), model.maxAngRate,
+                                model_tf(model, _cast(x, dtype)), model.maxAngRate,
                                 elev_R, dtype)
 
     return {'sep': sep, 'maxspeed': maxspd, 'minspeed': minspd, 'angrate': angrate}
@@ -434,17 +456,21 @@ def fd_jacobian(fun, x0, abs_step=SLSQP_EPS):
     return J
 
 
-def fd_jacobian_exact(fun_ld, x0, abs_step=SLSQP_EPS):
-    """The same quotient with f evaluated in np.longdouble on the *fp64*
-    perturbed points, i.e. the (almost) exactly rounded value of SciPy's
-    formula.  ``fun_ld`` must accept/return longdouble arrays."""
+def fd_jacobian_exact(fun_x, x0, abs_step=SLSQP_EPS, dtype=object):
+    """The same quotient with f evaluated in exact rational arithmetic
+    (dtype=object: fractions.Fraction; the fp64 tables and inputs are taken as
+    exact rationals) on the *fp64* perturbed points, i.e. the exactly rounded
+    value of SciPy's formula.  dtype=np.longdouble is a cheaper variant that is
+    only good to ~|f| * 1e-19 / h.  ``fun_x`` comes from make_callables(...,
+    dtype=dtype)."""
     x0 = np.asarray(x0, dtype=np.float64)
-    f0 = np.atleast_1d(fun_ld(x0.astype(np.longdouble)))
+    f0 = np.atleast_1d(fun_x(_cast(x0, dtype)))
     h, dx = fd_steps(x0, abs_step)
     J = np.empty((f0.size, x0.size))
     for k in range(x0.size):
         x1 = x0.copy()
         x1[k] = x0[k] + h[k]
-        f1 = np.atleast_1d(fun_ld(x1.astype(np.longdouble)))
-        J[:, k] = ((f1 - f0) / np.longdouble(dx[k])).astype(np.float64)
+        f1 = np.atleast_1d(fun_x(_cast(x1, dtype)))
+        q = (f1 - f0) / _num(float(dx[k]), dtype)
+        J[:, k] = np.array([float(v) for v in q]) if dtype is object else q.astype(np.float64)
     return J

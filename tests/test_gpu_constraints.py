@@ -66,7 +66,7 @@ def test_example1_golden(gopt, golden):
     for xi in (0, 1):
         for E in (0, 10, 100):
             _check_blocks(gopt, b, g["ex1_x%d" % xi], g, "ex1_x%d" % xi, E,
-                          ("sep", "maxspeed", "minspeed"))
+                          ("sep", "maxspeed", "minspeed", "angrate"))
 
 
 def test_c5_like_golden(gopt, golden):
@@ -77,7 +77,7 @@ def test_c5_like_golden(gopt, golden):
         x = g["c5_s%d_x" % seed]
         assert np.array_equal(b.reshapeVector(x), g["c5_s%d_y" % seed])
         for E in ((100, 0, 5) if seed == 0 else (100,)):
-            _check_blocks(gopt, b, x, g, "c5_s%d" % seed, E, ("sep", "maxspeed", "minspeed"))
+            _check_blocks(gopt, b, x, g, "c5_s%d" % seed, E, ("sep", "maxspeed", "minspeed", "angrate"))
 
 
 @pytest.mark.parametrize("dim,deg,N,E", [(1, 3, 5, 0), (2, 1, 4, 3), (3, 7, 9, 21), (2, 12, 7, 64),
@@ -127,3 +127,90 @@ def test_batched_and_pair_ranges(gopt):
 def test_single_vehicle_returns_none(gopt):
     b = gopt.BezOptimization(numVeh=1, dimension=2, degree=5, initPoints=[(0, 0)], finalPoints=[(1, 1)])
     assert b.temporalSeparationConstraints(np.zeros(b.nvar)) is None
+
+
+# --------------------------------------------------------------------------
+# A7: finite-difference Jacobians.  Judged against the exactly rounded quotient
+# (oracle evaluated in exact rational arithmetic on the fp64 points), tolerance 1e-9 relative
+# to the largest entry; the reference's own literal FD sits ~1e-7 away from
+# that value (its noise floor) and is checked at that level.
+JTOL = 1e-9
+
+
+def _jac_check(gopt, args, x, E, golden_J=None, names=("sep", "maxspeed", "minspeed")):
+    from oracle import bezier_oracle as O
+    b = gopt.BezOptimization(**args)
+    gopt.DEG_ELEV = E
+    fld = O.make_callables(O.Model(**args), E, dtype=object)
+    fns = {"sep": b.temporalSeparationConstraints_jac, "maxspeed": b.maxSpeedConstraints_jac,
+           "minspeed": b.minSpeedConstraints_jac}
+    for name in names:
+        J = fns[name](x)
+        Jex = O.fd_jacobian_exact(fld[name], x)
+        assert J.shape == Jex.shape
+        scale = np.abs(Jex).max()
+        assert np.abs(J - Jex).max() / scale < JTOL, name
+        # sparsity: rows that do not depend on x_k are exact zeros in both; entries that
+        # are zero only by cancellation (e.g. the fixed end speed of a Dubins curve w.r.t.
+        # tf) may be O(ulp) instead of 0
+        assert np.all(np.abs(Jex[J == 0]) <= 1e-13 * scale), name
+        assert np.all(np.abs(J[Jex == 0]) <= 1e-13 * scale), name
+        if golden_J is not None and name in golden_J:
+            Jref = golden_J[name]
+            assert np.abs(J - Jref).max() / scale < 5e-6        # reference FD noise floor
+            assert np.all(np.abs(Jref[J == 0]) <= 5e-6 * scale), name
+            # columns of variables that move no curve of a row are exact zeros in both
+            untouched = np.all(J == 0, axis=0)
+            assert np.all(Jref[:, untouched] == 0), name
+
+
+def test_jacobian_swarm(gopt, golden):
+    from oracle.make_golden import synthetic_swarm_args
+    g = golden("jacobian")
+    args, x = synthetic_swarm_args(6, deg=5, seed=11)
+    _jac_check(gopt, args, x, 10, {"sep": g["sw6_J_sep_E10"], "maxspeed": g["sw6_J_maxspeed_E10"]})
+
+
+def test_jacobian_dubins_timeopt_obstacles(gopt, golden):
+    from oracle.make_golden import dubins_problem_args
+    g = golden("jacobian")
+    args = dubins_problem_args(5, nobs=4, deg=6)
+    _jac_check(gopt, args, g["dub_x"], 8, {"sep": g["dub_J_sep_E8"], "maxspeed": g["dub_J_maxspeed_E8"]})
+
+
+def test_jacobian_example1(gopt, golden):
+    g = golden("jacobian")
+    args = dict(numVeh=2, dimension=2, degree=10, minimizeGoal='TimeOpt', maxSep=1, maxSpeed=5,
+                maxAngRate=1, initPoints=[(0, 5), (3, 0)], finalPoints=[(8, 4), (7, 10)],
+                initSpeeds=[1, 1], finalSpeeds=[1, 1], initAngs=[0, np.pi / 2],
+                finalAngs=[0, np.pi / 2], pointObstacles=[[3, 2], [6, 7]])
+    for E in (0, 10):
+        _jac_check(gopt, args, g["ex1_x"], E, {"sep": g["ex1_J_sep_E%d" % E],
+                                               "maxspeed": g["ex1_J_maxspeed_E%d" % E]})
+
+
+def test_jacobian_sweep_layout_matches_dense(gopt):
+    from oracle.make_golden import synthetic_swarm_args
+    args, x = synthetic_swarm_args(9, deg=7, seed=4)
+    b = gopt.BezOptimization(**args)
+    eng = b._engine(True)
+    E = 33
+    JT = eng.jac_separation(x, E, dense=True).cpu().numpy()          # [nvar, P*L]
+    sw = eng.jac_separation(x, E, dense=False).cpu().numpy()         # [nvar*(N-1), L]
+    N, L = eng.N, 2 * 7 + E + 1
+    sw = sw.reshape(eng.nvar, N - 1, L)
+    for k in range(eng.nvar):
+        v = k // (eng.dim * eng.ncols)
+        others = [u for u in range(N) if u != v]
+        for uu, u in enumerate(others):
+            i, j = min(v, u), max(v, u)
+            p = i * (2 * N - i - 1) // 2 + (j - i - 1)
+            assert np.array_equal(JT[k, p * L:(p + 1) * L], sw[k, uu])
+
+
+def test_angrate_rejects_3d(gopt):
+    from oracle.make_golden import synthetic_swarm_args
+    args, x = synthetic_swarm_args(3)
+    b = gopt.BezOptimization(**args)
+    with pytest.raises(ValueError):
+        b.maxAngularRateConstraints(x)

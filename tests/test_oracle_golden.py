@@ -144,7 +144,7 @@ def test_fd_jacobian_vs_reference_noise_floor(golden):
     assert np.array_equal(x, g["sw6_x"])
     m = O.Model(**args)
     f64 = O.make_callables(m, 10)
-    fld = O.make_callables(m, 10, dtype=np.longdouble)
+    fld = O.make_callables(m, 10, dtype=object)
     for name in ("sep", "maxspeed"):
         Jref = g["sw6_J_%s_E10" % name]
         Jlit = O.fd_jacobian(f64[name], x)
