@@ -111,55 +111,46 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------
-def cpu_port_worker(task):
-    """Oracle port (numpy restatement of the reference) on a block of pairs."""
+def cpu_baseline(args, x, E, target_seconds=12.0, threads=0):
+    """Times the plain-C restatement of the reference (oracle/bezier_oracle.c, all
+    host threads) on a bounded, contiguous sample of the C4 pair list and
+    extrapolates linearly to evals/s (pairs are independent and of equal cost).
+    The Python reference itself cannot travel to the GPU box; in the authoring
+    container it costs 23-34 us per pair per core, about
+    10x more than this port."""
     from oracle import bezier_oracle as O
-    y, pairs, dim, maxSep, E = task
-    t0 = time.perf_counter()
-    out = []
-    for (i, j) in pairs:
-        dv = y[i * dim:(i + 1) * dim] - y[j * dim:(j + 1) * dim]
-        out.append(O.elev(O.norm_square(dv), E)[0] - maxSep ** 2)
-    return time.perf_counter() - t0, len(pairs)
-
-
-def cpu_baseline(args, x, E, target_seconds=12.0, procs=None):
-    """Times the oracle port on a bounded sample of the C4 pairs on all host
-    cores and extrapolates to evals/s (pairs are independent and equal cost)."""
-    import multiprocessing as mp
-    from oracle import bezier_oracle as O
-    procs = procs or os.cpu_count() or 1
+    from oracle import c_oracle as C
     m = O.Model(**args)
     y = O.reshape_vector(m, x)
     N, dim = m.numVeh, m.dim
     P = N * (N - 1) // 2
-    rng = np.random.default_rng(0)
-    # calibrate on one core
-    cal = [(int(a), int(b)) for a, b in zip(rng.integers(0, N // 2, 200), rng.integers(N // 2, N, 200))]
-    O.elev(O.norm_square(y[:dim] - y[dim:2 * dim]), E)      # warm tables
-    tcal, _ = cpu_port_worker((y, cal, dim, m.maxSep, E))
-    per_pair = tcal / len(cal)
-    n_per_proc = max(200, int(target_seconds / per_pair))
-    tasks = []
-    for p in range(procs):
-        ii = rng.integers(0, N - 1, n_per_proc)
-        jj = np.minimum(ii + 1 + rng.integers(0, N - 1, n_per_proc) % np.maximum(N - 1 - ii, 1), N - 1)
-        tasks.append((y, list(zip(ii.tolist(), jj.tolist())), dim, m.maxSep, E))
+    L = 2 * m.deg + E + 1
+    threads = threads or C.max_threads()
+    cal_pairs = min(P, 65536)
+    out = np.empty(cal_pairs * L)
+    C.temporal_separation(y, N, dim, m.maxSep, E, 0, cal_pairs, nthreads=threads, out=out)   # warm + calibrate
     t0 = time.perf_counter()
-    if procs > 1:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(cpu_port_worker, tasks)
-    else:
-        res = [cpu_port_worker(tasks[0])]
-    wall = time.perf_counter() - t0
-    pairs_done = sum(r[1] for r in res)
-    pairs_per_s = pairs_done / wall
-    # one eval = P pairs (+ N speed rows, same per-row cost as a pair)
-    evals_per_s = pairs_per_s / (P + N)
-    return {"value": evals_per_s, "unit": "evals/s", "cores": procs, "kind": "port",
-            "sample": "%d of %d pairs of the C4 swarm (N=%d, deg %d, elev %d) on %d processes, "
-                      "%.1f s wall; numpy restatement of the reference (oracle/bezier_oracle.py), "
-                      "extrapolated linearly in pairs" % (pairs_done, P, N, m.deg, E, procs, wall)}, wall
+    C.temporal_separation(y, N, dim, m.maxSep, E, 0, cal_pairs, nthreads=threads, out=out)
+    per_pair = (time.perf_counter() - t0) / cal_pairs
+    chunk = min(P, 262144)
+    out = np.empty(chunk * L)
+    reps = max(1, int(target_seconds / (per_pair * chunk)))
+    done = 0
+    t0 = time.perf_counter()
+    for r in range(reps):
+        begin = (r * chunk) % max(1, P - chunk + 1)
+        C.temporal_separation(y, N, dim, m.maxSep, E, begin, chunk, nthreads=threads, out=out)
+        done += chunk
+    t_speed0 = time.perf_counter()
+    C.speed(y, N, dim, m.tf, E, -1.0, m.maxSpeed ** 2, nthreads=threads)
+    t_speed = time.perf_counter() - t_speed0
+    wall = time.perf_counter() - t0 - t_speed
+    sec_per_eval = wall / done * P + t_speed
+    return {"value": 1.0 / sec_per_eval, "unit": "evals/s", "cores": threads, "kind": "port",
+            "sample": "%d pair evaluations drawn from the %d pairs of the C4 swarm (N=%d, deg %d, elev %d) + all %d speed rows, "
+                      "%d threads, %.1f s wall; plain-C restatement of the reference "
+                      "(oracle/bezier_oracle.c: sub -> normSquare -> elev), extrapolated linearly in pairs"
+                      % (done, P, N, m.deg, E, N, threads, wall + t_speed)}, wall + t_speed
 
 
 # --------------------------------------------------------------------------
@@ -170,7 +161,8 @@ def run_reference(opts):
     args, x = synthetic_swarm(WORKLOAD["N"], WORKLOAD["deg"])
     E = WORKLOAD["elev"]
     vals, walls = [], []
-    per_step = max(2.0, min(20.0, 120.0 / max(1, opts.steps + opts.warmup)))
+    per_step = max(1.0, min(15.0, 120.0 / max(1, opts.steps + opts.warmup)))
+    cb = None
     for s in range(opts.warmup + opts.steps):
         cb, wall = cpu_baseline(args, x, E, target_seconds=per_step)
         if s >= opts.warmup:
@@ -201,6 +193,7 @@ def run_ours(opts):
     import torch
     import torch.distributed as dist
     from optimalbeziertrajectorygeneration_b200 import optimization as gopt
+    from optimalbeziertrajectorygeneration_b200 import sharding
     from optimalbeziertrajectorygeneration_b200.engine import num_pairs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,15 +217,15 @@ def run_ours(opts):
     out_sep = torch.empty((B, P, L), dtype=torch.float64, device=eng.device)
     out_spd = torch.empty((B, N, L), dtype=torch.float64, device=eng.device)
     pairmin = torch.empty((B, P), dtype=torch.float64, device=eng.device)
-    gathered = torch.empty((world * B, P), dtype=torch.float64, device=eng.device) if world > 1 else None
     max_speed2 = float(args["maxSpeed"]) ** 2
 
     def step():
         cpts, tf = eng.assemble(d_x, E)
         eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pairmin)
         eng.speed(cpts, tf, E, -1.0, max_speed2, out=out_spd)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, pairmin)
+        # the one collective of the path: every rank ends up with the whole
+        # [world*B, P] per-pair minimum (active-pair) matrix
+        return sharding.gather_pair_minima(pairmin, mode="batch")
     launches_per_step = 3       # assemble, fused pair kernel (values + per-pair min), speed kernel
 
     def barrier():
@@ -271,32 +264,51 @@ def run_ours(opts):
     kms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
     clocks = sampler.stop() if rank == 0 else None
 
-    # end to end through the reference-facing closures: host x in, host numpy out
-    e2e = None
-    if rank == 0 or world > 1:
-        gopt.DEG_ELEV = E
-        bezopt.zero_copy_results = True
-        sepf, spdf = bezopt.temporalSeparationConstraints, bezopt.maxSpeedConstraints
-        nE = max(2, min(opts.steps, 4))
-        for _ in range(2):
-            sepf(X[0]); spdf(X[0])
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(nE):
-            r1 = sepf(X[s % B]); r2 = spdf(X[s % B])
-        torch.cuda.synchronize()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": nE * world / dt, "unit": "evals/s",
-               "h2d_bytes_per_step": int(2 * x.size * 8), "d2h_bytes_per_step": int((r1.size + r2.size) * 8),
-               "evals_timed": nE * world,
-               "note": "BezOptimization.temporalSeparationConstraints(x)+maxSpeedConstraints(x): "
-                       "host x -> pinned H2D -> kernels -> D2H of the full constraint vector into pinned host memory"}
-        gopt.DEG_ELEV = 0
+    # end to end through the public host API (host X in pinned memory -> H2D ->
+    # kernels, every row materialised in HBM -> D2H of the step's result).
+    #  (a) evaluate_reduced: result = per-pair minima [B,P] + max-speed rows
+    #  (b) the reference-facing closures: result = the full constraint vector
+    gopt.DEG_ELEV = E
+    bezopt.zero_copy_results = True
+    nE = max(3, min(opts.steps, 20))
+    for _ in range(3):
+        red = bezopt.evaluate_reduced(X, elev=E)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(nE):
+        red = bezopt.evaluate_reduced(X, elev=E)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt_red = float(tt.item())
+    sepf, spdf = bezopt.temporalSeparationConstraints, bezopt.maxSpeedConstraints
+    nF = 3
+    for _ in range(2):
+        r1 = sepf(X[0]); r2 = spdf(X[0])
+    barrier()
+    t0 = time.perf_counter()
+    for s_ in range(nF):
+        r1 = sepf(X[s_ % B]); r2 = spdf(X[s_ % B])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt_full = float(tt.item())
+    e2e = {"value": nE * B * world / dt_red, "unit": "evals/s",
+           "h2d_bytes_per_step": int(X.size * 8),
+           "d2h_bytes_per_step": int((red["pairmin"].size + red["maxspeed"].size) * 8),
+           "steps_timed": nE,
+           "note": "BezOptimization.evaluate_reduced(X_host[B,nvar]): pinned H2D of X -> assemble -> fused pair "
+                   "kernel (all P*L values written to HBM + per-pair min) -> speed kernel -> D2H of the per-pair "
+                   "minima and max-speed rows; wall clock incl. Python",
+           "full_vector": {"value": nF * world / dt_full, "unit": "evals/s",
+                           "d2h_bytes_per_eval": int((r1.size + r2.size) * 8),
+                           "note": "temporalSeparationConstraints(x)+maxSpeedConstraints(x) returning the full "
+                                   "508 MB constraint vector to host memory (PCIe-bound)"}}
+    gopt.DEG_ELEV = 0
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -305,7 +317,7 @@ def run_ours(opts):
             peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        alg_bytes = 8.0 * B * (P * L + 2 * 3 * (deg + 1) * N)      # rows written + control points read
+        alg_bytes = 8.0 * B * (P * L + P + 34 * N)      # rows + per-pair minima written, control-point rows read
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         evals = B * world * opts.steps
         line = {"metric": "constraint+Jacobian evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s",
@@ -328,7 +340,7 @@ def run_ours(opts):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="evals (x vectors) per step per GPU")

@@ -155,6 +155,12 @@ int bez_jac_speed_sq_elev(const bez_plan *plan, const double *d_cpts, int N, int
                           const double *d_dx, const double *d_dir, int kdir, int dense,
                           double *d_out, int64_t ld, void *stream);
 
+/* Literal 2-point quotient (scipy/optimize/_numdiff.py:709-711) for constraint
+ * blocks without a closed form (angular rate): d_F [nvar+1][m] holds f(x0) in row
+ * 0 and f(x0 + h_k e_k) in row k+1; d_JT [nvar][m] = (F[k+1] - F[0]) / dx[k]. */
+int bez_fd_quotient(const double *d_F, const double *d_dx, int nvar, int64_t m,
+                    double *d_JT, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@ SIGNATURES = {
     "bez_angrate_tables_create": (I, [I, I, I, P, P, P, P, ctypes.POINTER(c_plan_p)]),
     "bez_angrate_tables_destroy": (I, [c_plan_p]),
     "bez_angrate_sq": (I, [c_plan_p, P, P, I, I, I, I, I, D, D, P, P]),
+    "bez_fd_quotient": (I, [P, P, I, L64, P, P]),
     "bez_jac_sepsq_elev": (I, [c_plan_p, P, I, I, I, I, P, P, I, I, P, L64, P]),
     "bez_jac_speed_sq_elev": (I, [c_plan_p, P, I, I, I, I, D, D, P, P, I, I, P, L64, P]),
 }

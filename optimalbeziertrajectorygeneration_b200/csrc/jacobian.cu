@@ -269,7 +269,31 @@ int fill_common(const bez_plan *plan, JacArgs &A, const double *d_cpts, const do
     return BEZ_OK;
 }
 
+// literal 2-point quotient for constraints without a closed form (angular rate):
+//   JT[k][r] = (F[k+1][r] - F[0][r]) / dx[k]      (_numdiff.py:709-711)
+__global__ void fd_quotient_kernel(const double *__restrict__ F, const double *__restrict__ dx,
+                                   int nvar, long long m, double *__restrict__ JT) {
+    const long long total = (long long)nvar * m;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long k = idx / m, r = idx - k * m;
+        JT[idx] = __ddiv_rn(__dsub_rn(F[(k + 1) * m + r], F[r]), __ldg(dx + k));
+    }
+}
+
 }  // namespace
+
+extern "C" int bez_fd_quotient(const double *d_F, const double *d_dx, int nvar, int64_t m,
+                               double *d_JT, void *stream) {
+    BEZ_REQUIRE(d_F && d_dx && d_JT, "NULL argument");
+    BEZ_REQUIRE(nvar >= 0 && m >= 0, "negative size");
+    if (nvar == 0 || m == 0) return BEZ_OK;
+    long long blocks = ((long long)nvar * m + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    fd_quotient_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_F, d_dx, nvar, m, d_JT);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
 
 extern "C" int bez_jac_sepsq_elev(const bez_plan *plan, const double *d_cpts, int N, int numVeh,
                                   int ncols, int offset, const double *d_dx, const double *d_dir,

@@ -325,3 +325,21 @@ class ConstraintEngine:
                    self.offset, tf, float(alpha), _ptr(d_dx), _ptr(dirs), kdir, int(dense), _ptr(out),
                    ld, _stream())
         return out
+
+    def jac_angrate(self, x, elev, alpha, beta):
+        """Literal '2-point' FD Jacobian of the angular-rate block: base point and
+        all nvar perturbed points are evaluated in one batched launch (what SciPy
+        does serially with the reference), then differenced on the device.
+        Returns J^T [nvar, numVeh*(4m+1)]."""
+        x = np.asarray(x, dtype=np.float64)
+        h, dx = self.fd_steps(x)
+        X = np.repeat(x[None, :], self.nvar + 1, axis=0)
+        idx = np.arange(self.nvar)
+        X[idx + 1, idx] = x + h
+        cpts, tf = self.assemble(self.upload(X), elev)
+        F = self.angrate(cpts, tf, elev, alpha, beta).reshape(self.nvar + 1, -1)
+        m = int(F.shape[1])
+        d_dx = torch.as_tensor(dx, device=self.device)
+        JT = torch.empty((self.nvar, m), dtype=F64, device=self.device)
+        _capi.call("bez_fd_quotient", _ptr(F), _ptr(d_dx), self.nvar, m, _ptr(JT), _stream())
+        return JT

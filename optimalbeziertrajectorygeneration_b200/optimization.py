@@ -194,6 +194,16 @@ class BezOptimization:
             return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
         return wrapper
 
+    @property
+    def maxAngularRateConstraints_jac(self):
+        """Batched literal FD (no closed form for the ratio): same noise floor
+        as SciPy differencing the reference (~1e-7 relative)."""
+        def wrapper(x):
+            eng = self._engine(with_obstacles=False)
+            JT = eng.jac_angrate(x, _deg_elev(), -1.0, float(self.model['maxAngRate']) ** 2)
+            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+        return wrapper
+
     # ------------------------------------------------------------------
     def generateGuess(self, std=0, seed=None):
         """optimization.py:189-240 (host logic; uses numpy's global RNG like
@@ -269,6 +279,42 @@ class BezOptimization:
                 res['minspeed'] = eng.speed(cpts, tf, E, 1.0, -float(self.model['minSpeed']) ** 2
                                             ).reshape(d_x.shape[0], -1)
         return res
+
+    def evaluate_reduced(self, X, elev=None):
+        """Additive API for swarms whose full constraint vector is consumed on the
+        device (508 MB per x at N=1024): host X [B, nvar] -> host arrays
+        ``pairmin`` [B, P] (min over each pair's elevated separation values; its
+        sign is the active-pair flag) and ``maxspeed`` [B, numVeh*L].  Every
+        separation row is still materialised in HBM and stays available as the
+        device tensor ``self.workspace['sep']`` until the next call."""
+        E = _deg_elev() if elev is None else int(elev)
+        eng = self._engine(with_obstacles=True)
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        B = X.shape[0]
+        P = _engine.num_pairs(eng.N)
+        L = 2 * self.model['deg'] + E + 1
+        ws = getattr(self, 'workspace', None)
+        if ws is None or ws.get('key') != (B, E):
+            ws = {'key': (B, E),
+                  'sep': torch.empty((B, P, L), dtype=torch.float64, device=eng.device),
+                  'pairmin': torch.empty((B, P), dtype=torch.float64, device=eng.device),
+                  'maxspeed': torch.empty((B, self.model['numVeh'], L), dtype=torch.float64,
+                                          device=eng.device)}
+            self.workspace = ws
+        cpts, tf = eng.assemble(eng.upload(X), E)
+        eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'], pairmin=ws['pairmin'])
+        eng.speed(cpts, tf, E, -1.0, float(self.model['maxSpeed']) ** 2, nveh=self.model['numVeh'],
+                  out=ws['maxspeed'])
+        # two async copies into pinned staging, one synchronisation
+        pm = eng._pinned_buf('pairmin', ws['pairmin'].numel())
+        sp = eng._pinned_buf('maxspeed', ws['maxspeed'].numel())
+        pm.copy_(ws['pairmin'].view(-1), non_blocking=True)
+        sp.copy_(ws['maxspeed'].view(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        pmh, sph = pm.numpy().reshape(B, P), sp.numpy().reshape(B, -1)
+        if not self.zero_copy_results:
+            pmh, sph = pmh.copy(), sph.copy()
+        return {'pairmin': pmh, 'maxspeed': sph}
 
     # objectives are added by the cost module (A14)
     def euclideanObjective(self, x):

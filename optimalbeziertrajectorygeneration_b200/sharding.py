@@ -1,0 +1,66 @@
+"""Multi-GPU sharding of the constraint path (one process per GPU,
+torch.distributed; NCCL over NVLink on the GPUs, gloo in the CPU tests).
+
+The reference has no parallelism at all; the units of this path
+are independent, so sharding needs no data-path collective:
+
+  * ``batch``  -- the finite-difference perturbations x + h_k e_k (or any batch
+    of optimisation vectors) are dealt out in contiguous blocks; each rank
+    evaluates all pairs for its own x's (weak scaling).
+  * ``pairs``  -- one x, the lexicographic pair list is cut into ``world``
+    contiguous, equally sized ranges (the C-ABI takes [pair_begin, npairs)), so
+    the output of rank r is exactly rows [begin_r, end_r) of the full vector.
+
+The only collective is one all-gather of the per-pair minimum (the active-pair
+source): after it every rank holds the whole [B_total, P] min-distance matrix.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def block_range(total, world, rank):
+    """Contiguous balanced block [begin, end) of ``total`` units for ``rank``."""
+    base, rem = divmod(int(total), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def pair_range(n_curves, world, rank):
+    """[pair_begin, pair_end) of the i<j pair list handled by ``rank``."""
+    return block_range(n_curves * (n_curves - 1) // 2, world, rank)
+
+
+def gather_pair_minima(local, mode="batch", total=None):
+    """All-gathers the per-pair minima.
+
+    mode 'batch': local is [B_local, P] (equal B_local on all ranks) -> [world*B_local, P]
+    mode 'pairs': local is [B, P_local] with possibly unequal P_local; ``total`` = P
+                  -> [B, P]   (padded all-gather, then the pad columns are dropped)
+    """
+    rank, world = world_info()
+    if world == 1:
+        return local
+    if mode == "batch":
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+    if mode != "pairs":
+        raise ValueError("mode must be 'batch' or 'pairs'")
+    B = local.shape[0]
+    width = -(-int(total) // world)                      # widest shard
+    padded = torch.zeros((B, width), dtype=local.dtype, device=local.device)
+    padded[:, :local.shape[1]] = local
+    buf = torch.empty((world, B, width), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf.view(world * B, width), padded)
+    parts = []
+    for r in range(world):
+        b, e = block_range(total, world, r)
+        parts.append(buf[r, :, :e - b])
+    return torch.cat(parts, dim=1)

@@ -214,3 +214,16 @@ def test_angrate_rejects_3d(gopt):
     b = gopt.BezOptimization(**args)
     with pytest.raises(ValueError):
         b.maxAngularRateConstraints(x)
+
+
+def test_jacobian_angrate_literal_fd(gopt, golden):
+    """The angular-rate Jacobian is the batched literal quotient: it must agree
+    with the reference's own FD Jacobian to the FD noise floor."""
+    from oracle.make_golden import dubins_problem_args
+    g = golden("jacobian")
+    b = gopt.BezOptimization(**dubins_problem_args(5, nobs=4, deg=6))
+    gopt.DEG_ELEV = 8
+    J = b.maxAngularRateConstraints_jac(g["dub_x"])
+    Jref = g["dub_J_angrate_E8"]
+    assert J.shape == Jref.shape
+    assert np.abs(J - Jref).max() / np.abs(Jref).max() < 1e-5
