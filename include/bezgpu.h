@@ -28,6 +28,7 @@
 #ifndef BEZGPU_H
 #define BEZGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -160,6 +161,76 @@ int bez_jac_speed_sq_elev(const bez_plan *plan, const double *d_cpts, int N, int
  * 0 and f(x0 + h_k e_k) in row k+1; d_JT [nvar][m] = (F[k+1] - F[0]) / dx[k]. */
 int bez_fd_quotient(const double *d_F, const double *d_dx, int nvar, int64_t m,
                     double *d_JT, void *stream);
+
+/* ---- single-curve algebra behind the bezier.Bezier methods, batched over
+ * independent rows/curves; tables are DEVICE arrays the caller built on the host
+ * with scipy.special.binom (same expressions as the reference).
+ *   bez_curve_elev   Bezier.elev        bezier.py:469-495   d_T = elevMatrix(n,R) [n+1][n+R+1]
+ *   bez_curve_diff   Bezier.diff        bezier.py:497-519   d_E1 = elevMatrix(n-1,1); d_T[rows/rows_per_T] = tf-t0
+ *   bez_curve_mul    Bezier.mul         bezier.py:376-432   d_W [m+1][n+1] = C(m,i)C(n,j)/C(m+n,i+j)
+ *   bez_curve_normsq Bezier.normSquare  bezier.py:869-889   d_cpts [curves][dim][n+1] -> [curves][2n+1] (x dim/2, Q1)
+ *   bez_curve_eval   Bezier.__call__/.curve -> deCasteljauCurve bezier.py:944-982 (bit exact, no FMA)
+ */
+int bez_curve_elev(const double *d_cpts, const double *d_T, int64_t rows, int n, int R,
+                   double *d_out, void *stream);
+int bez_curve_diff(const double *d_cpts, const double *d_E1, const double *d_T, int64_t rows,
+                   int64_t rows_per_T, int n, double *d_out, void *stream);
+int bez_curve_mul(const double *d_a, const double *d_b, const double *d_W, int64_t rows, int m, int n,
+                  double *d_out, void *stream);
+int bez_curve_normsq(const double *d_cpts, const double *d_W, int64_t curves, int dim, int n,
+                     double *d_out, void *stream);
+int bez_curve_eval(const double *d_cpts, const double *d_tau, int64_t rows, int n, int ntau,
+                   double t0, double tf, double *d_out, void *stream);
+
+/* ---- A8: Bezier.split -> deCasteljauSplit (bezier.py:533-572, 985-1027), bit exact.
+ *   d_cpts [count][dim][n+1]; d_tlocal [count] = (tDiv - t0)/(tf - t0); outputs same shape,
+ *   right half already in ascending order (bezier.py:563).  One warp per curve. */
+int bez_split(const double *d_cpts, const double *d_tlocal, int count, int dim, int n,
+              double *d_left, double *d_right, void *stream);
+
+/* ---- A9: Bezier.min / Bezier.max (bezier.py:631-667, 727-763), the intended
+ * algorithm (split at the extreme control point's local parameter; the reference
+ * extrapolates beyond depth 1).  d_rows [count][n+1]; d_status 1 = depth limit.
+ * d_scratch: bez_extrema_scratch_doubles(count, n, max_depth) doubles. */
+size_t bez_extrema_scratch_doubles(int count, int n, int max_depth);
+int bez_extrema(const double *d_rows, int count, int n, double tol, int maximum, int max_depth,
+                double *d_scratch, double *d_out, int *d_status, void *stream);
+
+/* ---- A10: gjkNew (gjk/gjk.py:229-360 and helpers :87-114, :397-477, :493-681).
+ *   d_poly1 [count][n1max][3], d_n1 [count] or NULL (= n1max each); likewise poly2.
+ *   d_flag: 1 distance available / 0 collision / -1 iteration limit;
+ *   d_p1, d_p2 [count][3], d_dist [count] (NaN unless flag == 1).  One warp per pair. */
+int bez_gjk(const double *d_poly1, const double *d_poly2, const int *d_n1, const int *d_n2,
+            int n1max, int n2max, int count, int *d_flag, double *d_p1, double *d_p2,
+            double *d_dist, void *stream);
+
+/* ---- A11: Bezier.minDist -> _minDist (bezier.py:840-852, 1283-1408, 1499-1516).
+ *   d_c1 [count][dim1][n1+1], d_c2 [count][dim2][n2+1] (2-D curves are z-padded);
+ *   d_out [count][3] = (alpha, t1, t2), NaN when d_status != 0; status bit 1 = a path
+ *   reached max_depth (the reference raises RecursionError there, SURVEY Q6: the search
+ *   is aborted), bit 4 = more than max_nodes GJK calls. */
+size_t bez_mindist_scratch_doubles(int count, int n1, int n2, int max_depth);
+int bez_mindist(const double *d_c1, const double *d_c2, int count, int dim1, int dim2, int n1,
+                int n2, double eps, int max_depth, long long max_nodes, double *d_scratch,
+                double *d_out, int *d_status, void *stream);
+
+/* ---- A12: minDist2Poly / collCheck / collCheck2Poly (bezier.py:1411-1496,
+ * 1535-1547, 1561-1651).  d_polys [count][mmax][3], d_npoly [count] or NULL.
+ *   mindist2poly d_out [count][5] = (alpha, t1, closest point xyz); status bit 1 =
+ *     depth limit, bit 2 = no closest point (the reference returns -1 there).
+ *   collcheck    d_out [count] = 1 (separated) / alpha (0.0 = contact) / -1 (depth 100)
+ *   collcheck2poly d_out [count] = 1 / 0; d_status 1 = node budget exhausted. */
+size_t bez_mindist2poly_scratch_doubles(int count, int n1, int max_depth);
+int bez_mindist2poly(const double *d_c1, const double *d_polys, const int *d_npoly, int count,
+                     int dim1, int n1, int mmax, double eps, int max_depth, long long max_nodes,
+                     double *d_scratch, double *d_out, int *d_status, void *stream);
+size_t bez_collcheck_scratch_doubles(int count, int n1, int n2);
+int bez_collcheck(const double *d_c1, const double *d_c2, int count, int dim1, int dim2, int n1,
+                  int n2, double eps, double *d_scratch, double *d_out, void *stream);
+size_t bez_collcheck2poly_scratch_doubles(int count, int n1);
+int bez_collcheck2poly(const double *d_c1, const double *d_polys, const int *d_npoly, int count,
+                       int dim1, int n1, int mmax, long long max_nodes, double *d_scratch,
+                       double *d_out, int *d_status, void *stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ UNITS = [
     ("constraints.cu", []),
     ("jacobian.cu", []),
     ("angrate.cu", []),
+    ("curveops.cu", []),
     ("geometry.cu", ["-fmad=false"]),
 ]
 

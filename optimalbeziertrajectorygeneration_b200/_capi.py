@@ -45,6 +45,23 @@ SIGNATURES = {
     "bez_angrate_tables_create": (I, [I, I, I, P, P, P, P, ctypes.POINTER(c_plan_p)]),
     "bez_angrate_tables_destroy": (I, [c_plan_p]),
     "bez_angrate_sq": (I, [c_plan_p, P, P, I, I, I, I, I, D, D, P, P]),
+    "bez_curve_elev": (I, [P, P, L64, I, I, P, P]),
+    "bez_curve_diff": (I, [P, P, P, L64, L64, I, P, P]),
+    "bez_curve_mul": (I, [P, P, P, L64, I, I, P, P]),
+    "bez_curve_normsq": (I, [P, P, L64, I, I, P, P]),
+    "bez_curve_eval": (I, [P, P, L64, I, I, D, D, P, P]),
+    "bez_split": (I, [P, P, I, I, I, P, P, P]),
+    "bez_extrema_scratch_doubles": (ctypes.c_size_t, [I, I, I]),
+    "bez_extrema": (I, [P, I, I, D, I, I, P, P, P, P]),
+    "bez_gjk": (I, [P, P, P, P, I, I, I, P, P, P, P, P]),
+    "bez_mindist_scratch_doubles": (ctypes.c_size_t, [I, I, I, I]),
+    "bez_mindist": (I, [P, P, I, I, I, I, I, D, I, ctypes.c_longlong, P, P, P, P]),
+    "bez_mindist2poly_scratch_doubles": (ctypes.c_size_t, [I, I, I]),
+    "bez_mindist2poly": (I, [P, P, P, I, I, I, I, D, I, ctypes.c_longlong, P, P, P, P]),
+    "bez_collcheck_scratch_doubles": (ctypes.c_size_t, [I, I, I]),
+    "bez_collcheck": (I, [P, P, I, I, I, I, I, D, P, P, P]),
+    "bez_collcheck2poly_scratch_doubles": (ctypes.c_size_t, [I, I]),
+    "bez_collcheck2poly": (I, [P, P, P, I, I, I, I, ctypes.c_longlong, P, P, P, P]),
     "bez_fd_quotient": (I, [P, P, I, L64, P, P]),
     "bez_jac_sepsq_elev": (I, [c_plan_p, P, I, I, I, I, P, P, I, I, P, L64, P]),
     "bez_jac_speed_sq_elev": (I, [c_plan_p, P, I, I, I, I, D, D, P, P, I, I, P, L64, P]),

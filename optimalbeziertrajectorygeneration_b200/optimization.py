@@ -127,6 +127,29 @@ class BezOptimization:
             return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
         return wrapper
 
+    def spatialSeparationConstraints(self, x):
+        """optimization.py:109-133: all pairs among the vehicles and the shape
+        obstacles (Bezier objects), minDist - maxSep; like the reference the
+        (alpha, t1, t2) tuple is kept, so the result is [npairs, 3].
+        All pairs run in one launch (one warp per pair)."""
+        from . import bezier as _bez
+        numVeh = self.model['numVeh']
+        dim = self.model['dim']
+        maxSep = self.model['maxSep']
+        y = self.reshapeVector(x)
+        curves = [np.ascontiguousarray(y[i * dim:(i + 1) * dim, :]) for i in range(numVeh)]
+        for obstacle in (self.shapeObstacles or []):
+            curves.append(np.ascontiguousarray(obstacle.cpts, dtype=np.float64))
+        n = len(curves)
+        shapes = {c.shape for c in curves}
+        if len(shapes) != 1:
+            raise ValueError('all vehicles and shape obstacles must share dimension and degree')
+        A = np.stack([curves[i] for i in range(n) for j in range(i + 1, n)])
+        Bc = np.stack([curves[j] for i in range(n) for j in range(i + 1, n)])
+        out, status = _bez.min_dist_batch(A, Bc, max_nodes=1 << 18)
+        self.last_status = status
+        return out - maxSep
+
     @property
     def minSpeedConstraints(self):
         """optimization.py:135-151 -> _minSpeedConstraints (:349-384)."""
