@@ -182,6 +182,16 @@ int bez_curve_normsq(const double *d_cpts, const double *d_W, int64_t curves, in
 int bez_curve_eval(const double *d_cpts, const double *d_tau, int64_t rows, int n, int ntau,
                    double t0, double tf, double *d_out, void *stream);
 
+/* ---- A14: cost callables (optimization.py:287-308, 462-519) on assembled control
+ * points d_cpts [B][N][S]; d_out [B].  euclidean = total control-polygon length
+ * (_euclideanObjective; for dim 2 the reference reads an uninitialised third
+ * component, SURVEY Q10 -- here it is 0); accel = sum of the control points of
+ * elev(normSquare(diff(diff(pos))), E) over the vehicles (_minAccelObjective). */
+int bez_objective_euclidean(const bez_plan *plan, const double *d_cpts, int B, int N, int numVeh,
+                            double *d_out, void *stream);
+int bez_objective_accel(const bez_plan *plan, const double *d_cpts, const double *d_tf, int B,
+                        int N, int numVeh, double *d_out, void *stream);
+
 /* ---- A8: Bezier.split -> deCasteljauSplit (bezier.py:533-572, 985-1027), bit exact.
  *   d_cpts [count][dim][n+1]; d_tlocal [count] = (tDiv - t0)/(tf - t0); outputs same shape,
  *   right half already in ascending order (bezier.py:563).  One warp per curve. */

@@ -78,6 +78,82 @@ __global__ void normsq_kernel(const double *c, const double *W, long long curves
     }
 }
 
+// ---- cost callables (A14) -----------------------------------------------------
+__device__ double block_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    return t;       // valid in thread 0
+}
+
+// _euclideanObjective (optimization.py:462-489): total control-polygon length.
+// cpts [B][N][S]; one block per evaluation point.
+__global__ void euclid_kernel(const double *cpts, int N, int S, int numVeh, int dim, int n1, double *out) {
+    __shared__ double red[32];
+    const double *base = cpts + (size_t)blockIdx.x * N * S;
+    double acc = 0.0;
+    const int segs = numVeh * (n1 - 1);
+    for (int s = threadIdx.x; s < segs; s += blockDim.x) {
+        const int v = s / (n1 - 1), i = s - v * (n1 - 1);
+        double q = 0.0;
+        for (int d = 0; d < dim; ++d) {
+            const double t = base[(size_t)v * S + d * n1 + i + 1] - base[(size_t)v * S + d * n1 + i];
+            q = fma(t, t, q);
+        }
+        acc += sqrt(q);
+    }
+    const double tot = block_sum(acc, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = tot;
+}
+
+// _minAccelObjective (optimization.py:503-519): sum over vehicles of the control
+// points of elev(normSquare(diff(diff(pos))), E).  T = elevMatrix(2n, E) [2n+1][L].
+__global__ void accel_kernel(const double *cpts, const double *tf, const double *W, const double *E1,
+                             const double *T, int N, int S, int numVeh, int dim, int n1, int L, double *out) {
+    __shared__ double red[32];
+    const int n = n1 - 1;
+    const double *base = cpts + (size_t)blockIdx.x * N * S;
+    const double val = (double)n / tf[blockIdx.x];
+    double acc = 0.0;
+    for (int v = threadIdx.x; v < numVeh; v += blockDim.x) {
+        double a[3][32];
+        for (int d = 0; d < dim; ++d) {
+            double p[32], q[32];
+            for (int k = 0; k < n1; ++k) p[k] = base[(size_t)v * S + d * n1 + k];
+            for (int rep = 0; rep < 2; ++rep) {                 // diff twice
+                for (int k = 0; k < n1; ++k) {
+                    double r = 0.0;
+                    if (k < n) r = (p[k] * (-val) + p[k + 1] * val) * E1[(size_t)k * n1 + k];
+                    if (k > 0) r = (p[k - 1] * (-val) + p[k] * val) * E1[(size_t)(k - 1) * n1 + k] + r;
+                    q[k] = r;
+                }
+                for (int k = 0; k < n1; ++k) p[k] = q[k];
+            }
+            for (int k = 0; k < n1; ++k) a[d][k] = p[k];
+        }
+        for (int k = 0; k <= 2 * n; ++k) {
+            const int ilo = k - n > 0 ? k - n : 0, ihi = k < n ? k : n;
+            double s = 0.0;
+            for (int i = ilo; i <= ihi; ++i) {
+                double g = 0.0;
+                for (int d = 0; d < dim; ++d) g = fma(a[d][i], a[d][k - i], g);
+                s = fma(W[(size_t)i * n1 + (k - i)], g, s);
+            }
+            s = (s * (double)dim) / 2.0;
+            double rs = 0.0;
+            for (int i = 0; i < L; ++i) rs += T[(size_t)k * L + i];
+            acc = fma(s, rs, acc);
+        }
+    }
+    const double tot = block_sum(acc, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = tot;
+}
+
 inline unsigned blocks_for(long long total) {
     long long b = (total + 255) / 256;
     if (b > 148 * 32) b = 148 * 32;
@@ -126,6 +202,29 @@ extern "C" int bez_curve_normsq(const double *d_cpts, const double *d_W, int64_t
     if (curves == 0) return BEZ_OK;
     normsq_kernel<<<blocks_for(curves * (2 * n + 1)), 256, 0, (cudaStream_t)stream>>>(d_cpts, d_W, curves, dim,
                                                                                       n + 1, d_out);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
+
+extern "C" int bez_objective_euclidean(const bez_plan *plan, const double *d_cpts, int B, int N, int numVeh,
+                                       double *d_out, void *stream) {
+    BEZ_REQUIRE(plan && d_cpts && d_out, "NULL argument");
+    BEZ_REQUIRE(B >= 0 && numVeh >= 1 && numVeh <= N, "bad sizes");
+    if (B == 0) return BEZ_OK;
+    const int n1 = plan->n + 1, S = (plan->dim * n1 + 1) / 2 * 2;
+    euclid_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_cpts, N, S, numVeh, plan->dim, n1, d_out);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
+
+extern "C" int bez_objective_accel(const bez_plan *plan, const double *d_cpts, const double *d_tf, int B,
+                                   int N, int numVeh, double *d_out, void *stream) {
+    BEZ_REQUIRE(plan && d_cpts && d_tf && d_out, "NULL argument");
+    BEZ_REQUIRE(B >= 0 && numVeh >= 1 && numVeh <= N, "bad sizes");
+    if (B == 0) return BEZ_OK;
+    const int n1 = plan->n + 1, S = (plan->dim * n1 + 1) / 2 * 2;
+    accel_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(d_cpts, d_tf, plan->d_W, plan->d_E1, plan->d_T, N, S,
+                                                     numVeh, plan->dim, n1, plan->L, d_out);
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;
 }

@@ -339,12 +339,33 @@ class BezOptimization:
             pmh, sph = pmh.copy(), sph.copy()
         return {'pairmin': pmh, 'maxspeed': sph}
 
-    # objectives are added by the cost module (A14)
+    # -- cost callables (A14, optimization.py:287-308) -----------------------
+    def _objective(self, x, kind):
+        eng = self._engine(with_obstacles=False)
+        E = _deg_elev()
+        d_x = eng.upload(x)
+        cpts, tf = eng.assemble(d_x, E)
+        out = torch.empty((d_x.shape[0],), dtype=torch.float64, device=eng.device)
+        plan = eng.plan(E)
+        if kind == 'euclidean':
+            _engine._capi.call("bez_objective_euclidean", plan.handle, _engine._ptr(cpts), int(d_x.shape[0]),
+                               eng.N, eng.numVeh, _engine._ptr(out), _engine._stream())
+        else:
+            # the reference passes model['tf'] here even for time-optimal problems
+            tfm = torch.full_like(tf, float(self.model['tf']))
+            _engine._capi.call("bez_objective_accel", plan.handle, _engine._ptr(cpts), _engine._ptr(tfm),
+                               int(d_x.shape[0]), eng.N, eng.numVeh, _engine._ptr(out), _engine._stream())
+        return float(out[0].item())
+
     def euclideanObjective(self, x):
-        raise NotImplementedError
+        """optimization.py:287-292 -> _euclideanObjective (:462-489)"""
+        return self._objective(x, 'euclidean')
 
     def accelObjective(self, x):
-        raise NotImplementedError
+        """optimization.py:294-300 -> _minAccelObjective (:503-519)"""
+        return self._objective(x, 'accel')
 
     def jerkObjective(self, x):
-        raise NotImplementedError
+        """optimization.py:302-308: the reference's _minJerkObjective is an @njit
+        over Python objects and raises a numba TypingError when called."""
+        raise NotImplementedError("the reference's jerk objective cannot run (numba TypingError); not provided")

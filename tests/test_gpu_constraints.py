@@ -227,3 +227,26 @@ def test_jacobian_angrate_literal_fd(gopt, golden):
     Jref = g["dub_J_angrate_E8"]
     assert J.shape == Jref.shape
     assert np.abs(J - Jref).max() / np.abs(Jref).max() < 1e-5
+
+
+def test_objectives(gopt, golden):
+    """A14: cost callables (swarm Euclidean objective at x0 from SURVEY section 4)."""
+    from oracle.make_golden import synthetic_swarm_args
+    g = golden("constraints")
+    gopt.DEG_ELEV = 0
+    b = gopt.BezOptimization(numVeh=36, dimension=3, degree=5, minimizeGoal='Euclidean', maxSep=0.9,
+                             initPoints=g["swarm_initPts"], finalPoints=g["swarm_finalPts"])
+    assert b.objectiveFunction(g["swarm_x0"]) == pytest.approx(382.0101330471013, rel=1e-13)
+    args, x = synthetic_swarm_args(5, deg=6, seed=3)
+    for goal in ("Euclidean", "Accel"):
+        a = dict(args)
+        a["minimizeGoal"] = goal
+        bb = gopt.BezOptimization(**a)
+        assert bb.objectiveFunction(x) == pytest.approx(float(g["obj_%s" % goal]), rel=1e-12)
+    a = dict(args)
+    a["minimizeGoal"] = "nonsense"
+    with pytest.raises(ValueError):
+        gopt.BezOptimization(**a).objectiveFunction
+    tb = gopt.BezOptimization(numVeh=1, dimension=2, degree=5, minimizeGoal='TimeOpt', initPoints=[(0, 0)],
+                              finalPoints=[(1, 1)])
+    assert tb.objectiveFunction(np.arange(9.0)) == 8.0
