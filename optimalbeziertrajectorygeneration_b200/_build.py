@@ -25,6 +25,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
 UNITS = [
     ("plan.cu", []),
     ("constraints.cu", []),
+    ("constraints_mma.cu", []),
     ("jacobian.cu", []),
     ("angrate.cu", []),
     ("curveops.cu", []),
@@ -47,7 +48,15 @@ def _stale(target, sources):
 
 
 def build(force=False, verbose=False):
+    """Full build, or -- with BEZGPU_ONLY_N=<degree> in the environment -- a development
+    build whose fused kernels are instantiated for that degree only (seconds instead
+    of minutes).  The flavor of the linked library is recorded in libbezgpu.flavor so a
+    later full build() always relinks over a development library."""
     nvcc = _nvcc()
+    only_n = os.environ.get("BEZGPU_ONLY_N", "")
+    flavor = "n" + only_n if only_n else "full"
+    suffix = "." + flavor + ".o" if only_n else ".o"
+    dev = ["-DBEZ_ONLY_N=" + only_n] if only_n else []
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(ROOT, "include", "bezgpu.h"))
     objs = []
@@ -56,10 +65,10 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, name)
         if not os.path.exists(src):
             continue
-        obj = os.path.join(CSRC, name[:-3] + ".o")
+        obj = os.path.join(CSRC, name[:-3] + suffix)
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + ARCH + COMMON + extra + dev + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((name, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for name, cmd, p in procs:
         out, _ = p.communicate()
@@ -67,9 +76,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (name, " ".join(cmd)))
-    if force or procs or _stale(LIB, objs):
+    stamp = os.path.join(PKG, "libbezgpu.flavor")
+    linked = open(stamp).read().strip() if os.path.exists(stamp) else ""
+    if force or procs or _stale(LIB, objs) or linked != flavor:
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
+        with open(stamp, "w") as f:
+            f.write(flavor + "\n")
     return LIB
 
 

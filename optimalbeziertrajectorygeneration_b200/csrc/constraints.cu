@@ -21,24 +21,12 @@
 //     outputs instead of 2(2n+1), and each warp emits two 256-byte coalesced
 //     streaming stores per item.  Nothing but the final L values per item ever
 //     goes to HBM.
-#include "sq_elev_core.cuh"
+#include <stdlib.h>
+
+#include "sq_elev_stage1.cuh"
 
 namespace {
 using namespace bezcore;
-
-enum Mode { PAIR = 0, SPEED = 1 };
-
-struct SqElevArgs {
-    const double *cpts;     // [B][N][S]  S = dim*(n+1) rounded up to even
-    const double *tf;       // [B] (SPEED)
-    const double *PQ;       // [2n+1][LhPad]
-    double *out;            // [B][nitems][L]
-    double *itemmin;        // [B][nitems] or null
-    long long item_begin;   // first pair / vehicle handled
-    long long nitems;       // pairs / vehicles per evaluation point
-    int B, N, L, Lh, LhPad;
-    double alpha, beta;     // out = alpha * value + beta   (alpha = +-1)
-};
 
 // One warp = one tile of 32 items.  No block-wide barriers in the main loop: the
 // warps of a block only share the (read-only) staged elevation table.
@@ -79,60 +67,8 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
 
         // ------------------------- stage 1: lane = item -------------------------
         {
-            // lanes past the end recompute the last item so every staged row is finite
-            const int li = lane < cnt ? lane : cnt - 1;
-            const double *base = A.cpts + (size_t)b * bstride;
-            double a[DIM][NC];
-            if (MODE == PAIR) {
-                int vi, vj;
-                bez_pair_decode(A.item_begin + t0 + li, A.N, vi, vj);
-                const double2 *pi = reinterpret_cast<const double2 *>(base + (size_t)vi * S);
-                const double2 *pj = reinterpret_cast<const double2 *>(base + (size_t)vj * S);
-                double *af = &a[0][0];
-#pragma unroll
-                for (int q = 0; q < S / 2; ++q) {                      // Bezier.sub
-                    const double2 u = __ldg(pi + q), w = __ldg(pj + q);
-                    if (2 * q < DIM * NC) af[2 * q] = u.x - w.x;
-                    if (2 * q + 1 < DIM * NC) af[2 * q + 1] = u.y - w.y;
-                }
-            } else {
-                const int v = (int)(A.item_begin + t0 + li);
-                const double val = (double)N_ / __ldg(A.tf + b);       // diffMatrix: n/tf
-                const double2 *pv = reinterpret_cast<const double2 *>(base + (size_t)v * S);
-                double ptf[S];
-#pragma unroll
-                for (int q = 0; q < S / 2; ++q) {
-                    const double2 u = __ldg(pv + q);
-                    ptf[2 * q] = u.x;
-                    ptf[2 * q + 1] = u.y;
-                }
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) {
-                    double dd[NC];
-#pragma unroll
-                    for (int k = 0; k < N_; ++k)                       // np.dot(cpts, Dm)
-                        dd[k] = ptf[d * NC + k] * (-val) + ptf[d * NC + k + 1] * val;
-                    dd[N_] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {                     // .elev(1) back to degree n
-                        double q = dd[k] * DW.lo[k];
-                        if (k > 0) q = dd[k - 1] * DW.hi[k] + q;
-                        a[d][k] = q;
-                    }
-                }
-            }
             double s[2 * N_ + 1];
-#pragma unroll
-            for (int k = 0; k <= 2 * N_; ++k) s[k] = 0.0;
-#pragma unroll
-            for (int i = 0; i < NC; ++i)
-#pragma unroll
-                for (int j = i; j < NC; ++j) {
-                    double g = a[0][i] * a[0][j];
-#pragma unroll
-                    for (int d = 1; d < DIM; ++d) g = fma(a[d][i], a[d][j], g);
-                    s[i + j] = fma(PW.w[widx<N_>(i, j)], g, s[i + j]);
-                }
+            stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, t0, lane < cnt ? lane : cnt - 1, s);
             double2 *row = rows + (size_t)lane * RS;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
@@ -291,8 +227,12 @@ template <int MODE>
 int dispatch_degree(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     switch (plan->n) {
 #define CASE(n_) case n_: return dispatch_dim<n_, MODE>(plan, A, st);
+#ifdef BEZ_ONLY_N   /* development builds: one degree only (fast compile) */
+        CASE(BEZ_ONLY_N)
+#else
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
         CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#endif
 #undef CASE
     }
     bez_set_error("degree %d has no fused kernel instantiation (1..16 supported)", plan->n);
@@ -316,6 +256,7 @@ extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, i
     A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
     A.alpha = 1.0; A.beta = -maxSep2;
+    if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, PAIR, (cudaStream_t)stream);
     return dispatch_degree<PAIR>(plan, A, (cudaStream_t)stream);
 }
 
@@ -332,6 +273,7 @@ extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, con
     A.item_begin = veh_begin; A.nitems = nveh; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
     A.alpha = alpha; A.beta = beta;
+    if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, SPEED, (cudaStream_t)stream);
     return dispatch_degree<SPEED>(plan, A, (cudaStream_t)stream);
 }
 

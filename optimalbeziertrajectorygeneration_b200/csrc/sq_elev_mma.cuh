@@ -1,0 +1,258 @@
+// Stage 2 of the fused "square -> fold -> elevate" kernels on the fp64 tensor
+// path (DMMA.8x8x4, mma.sync.m8n8k4.f64) with a TMA bulk-store epilogue.
+//
+// Why: the column-stationary DFMA sweep of sq_elev_core.cuh streams every item's
+// folded row through broadcast LDS.128 -- 25 L1 data-pipe wavefronts and 5.6 KB of
+// LSU->RF writeback per item, which ncu showed to be the binding unit (70 % of the
+// L1 data pipe at 60 % of HBM, profiles/r01_ncu_pair_kernel_dfma.txt).  One DMMA
+// does the work of 8 warp-wide DFMAs with all operands in registers, so the same
+// fp64 pipe time (DMMA and DFMA share one 64 FMA/clk/SM pipe, tools/pipe_bench.cu)
+// needs ~6x fewer issue slots and no operand traffic; the 8 x L output block of an
+// m-tile is staged in shared memory in its final HBM layout and leaves the SM as a
+// single cp.async.bulk (TMA) store instead of ~30 LSU store wavefronts.
+//
+// GEMM view per warp tile of 32 items (folding of sq_elev_core.cuh kept):
+//     se[item][c] = beta + sum_j e[item][j] P[j][c]        M = items   (4 m-tiles of 8)
+//     so[item][c] =        sum_j o[item][j] Q[j][c]        N = column pairs (<= 8 n-tiles of 8)
+//     out[item][c] = se + so,  out[item][L-1-c] = se - so  K = folded index j (k-steps of 4)
+// Fragment ownership (PTX ISA, mma.m8n8k4.f64): lane = 4 g + t holds A[g][t],
+// B[t][g], C[g][2t], C[g][2t+1].
+#pragma once
+#include "sq_elev_core.cuh"
+
+namespace bezmma {
+using bezcore::dmin;
+
+// Staged item row: e_j at slot_e(j), o_j at slot_o(j), stride kRowStride doubles.
+// With slot = 4 (j mod 4) + j / 4 the A-fragment load of a k-step (lane (g,t) reads
+// row g, j = 4 ks + t) hits double-bank (g + 4 t + ks) mod 16: conflict free per
+// half-warp; the odd row stride keeps the lane = item stores of stage 1 conflict
+// free as well.  Slots that no j maps to stay zero (zeroed once per kernel).
+constexpr int kRowStride = 33;
+constexpr int kRowsDoubles = 32 * kRowStride;      // 8448 B per warp (multiple of 16 B)
+__host__ __device__ constexpr int slot_e(int j) { return 4 * (j & 3) + (j >> 2); }
+__host__ __device__ constexpr int slot_o(int j) { return 16 + slot_e(j); }
+
+template <int N_> struct Geom {
+    static constexpr int KE = (N_ + 1 + 3) / 4;    // k-steps over e_0..e_n
+    static constexpr int KO = (N_ + 3) / 4;        // k-steps over o_0..o_{n-1}
+    static_assert(KE <= 4, "slot_e needs 4 ks + t < 16: degree <= 15");
+};
+
+// Column pair owned by element nn of n-tile ni.  Two n-tiles interleave over 16
+// consecutive columns so that the C-fragment stores (lane (g,t): columns c0, c0+1,
+// c0 = base + 4 t, row g, row pitch L doubles) touch double-banks g L + 4 t + const:
+// conflict free per half-warp whenever L is odd (E even), 2 wavefronts per STS.64.
+__host__ __device__ constexpr int col_of(int ni, int nn) {
+    return 16 * (ni >> 1) + 2 * (ni & 1) + 4 * (nn >> 1) + (nn & 1);
+}
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Monotone map double -> signed 64-bit integer (an involution on the bit pattern), so
+// that minima can be taken on the integer pipe instead of DSETP on the fp64 pipe.
+__device__ __forceinline__ long long order_key_bits(long long b) {
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ long long order_key(double v) { return order_key_bits(__double_as_longlong(v)); }
+
+// --- TMA bulk store (shared::cta -> global), bulk-group completion ----------------
+__device__ __forceinline__ void bulk_store(double *gdst, unsigned ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(PENDING) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Folded elevation weights in B-fragment order, register resident for the whole kernel.
+template <int N_> struct BFrags {
+    double p[8][Geom<N_>::KE];
+    double q[8][Geom<N_>::KO > 0 ? Geom<N_>::KO : 1];
+};
+
+template <int N_>
+__device__ __forceinline__ void load_bfrags(BFrags<N_> &B, const double *__restrict__ PQ, int Lh, int LhPad,
+                                            int lane) {
+    constexpr int NC = N_ + 1;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        const int col = col_of(ni, g);
+        const bool live = col < Lh;
+#pragma unroll
+        for (int ks = 0; ks < Geom<N_>::KE; ++ks) {
+            const int j = 4 * ks + t;
+            B.p[ni][ks] = (live && j <= N_) ? __ldg(PQ + (size_t)j * LhPad + col) : 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < Geom<N_>::KO; ++ks) {
+            const int j = 4 * ks + t;
+            B.q[ni][ks] = (live && j < N_) ? __ldg(PQ + (size_t)(NC + j) * LhPad + col) : 0.0;
+        }
+    }
+}
+
+// Per-lane constants of the epilogue, computed once per kernel.
+struct LaneGeom {
+    int g, t;
+    unsigned live;      // bit 2 (ni - 4) + c : column 16 (ni >> 1) + 2 (ni & 1) + 4 t + c < Lh  (ni = 4..7)
+};
+__device__ __forceinline__ LaneGeom lane_geom(int lane, int Lh) {
+    LaneGeom G;
+    G.g = lane >> 2;
+    G.t = lane & 3;
+    G.live = 0;
+#pragma unroll
+    for (int ni = 4; ni < 8; ++ni)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (16 * (ni >> 1) + 2 * (ni & 1) + 4 * G.t + c < Lh) G.live |= 1u << (2 * (ni - 4) + c);
+    return G;
+}
+
+// One warp tile: rows = staged (e,o) rows of 32 items, obuf = 2 x [8][L] doubles of
+// staging (+ 32 doubles of sink for dead columns), obuf_s = its shared-window address,
+// outg = global address of the tile's first output row (rows contiguous, pitch L),
+// ming = per-item minimum (MINMODE != 0).  seq counts m-tiles over the kernel's
+// lifetime and selects the staging buffer (at most one bulk read is left pending).
+//
+// Schedule of one m-tile (8 items): the n-tiles are processed in pairs; the 12 DMMAs of
+// pair p+1 (4 independent accumulator chains, round-robin over the k-steps) are issued
+// before the epilogue of pair p, so the fp64 pipe always has independent work queued
+// behind the DADD/STS of the epilogue (in-order issue: without this the epilogue waits
+// out the full DMMA latency, 38 % "wait" stalls in profiles/r01_ncu_pair_kernel_mma_v1).
+template <int N_, int MINMODE>
+__device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
+                                         const BFrags<N_> &B, const LaneGeom &G,
+                                         double *__restrict__ outg, double *__restrict__ ming, int cnt,
+                                         int L, int Lh, double beta, int lane, unsigned &seq) {
+    constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO;
+    const int g = G.g, t = G.t;
+    const int M = L - 1;
+    double mnv[4];
+    long long mkv[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) { mnv[mi] = INFINITY; mkv[mi] = 0x7fffffffffffffffLL; }
+    double *const sink = obuf + 16 * L + lane;
+    const double *ar = rows + g * kRowStride + 4 * t;
+    double aE[KE], aO[KO > 0 ? KO : 1];
+#pragma unroll
+    for (int ks = 0; ks < KE; ++ks) aE[ks] = ar[ks];
+#pragma unroll
+    for (int ks = 0; ks < KO; ++ks) aO[ks] = ar[16 + ks];
+
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        if (8 * mi >= cnt) break;
+        const unsigned par = seq & 1u;
+        ++seq;
+        double *ob = obuf + (size_t)par * 8 * L;
+        double *of = ob + g * L + 4 * t;           // forward cursor of this lane (column 4 t of row g)
+        double *om = ob + g * L + M - 4 * t;       // mirror cursor
+        double mn = INFINITY;
+        long long mk = 0x7fffffffffffffffLL;
+
+        double C[2][2][4];
+        auto mma_pair = [&](int p, double (&c)[2][4]) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { c[u][0] = beta; c[u][1] = beta; c[u][2] = 0.0; c[u][3] = 0.0; }
+#pragma unroll
+            for (int ks = 0; ks < KE; ++ks) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) dmma884(c[u][0], c[u][1], aE[ks], B.p[2 * p + u][ks]);
+                if (ks < KO) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) dmma884(c[u][2], c[u][3], aO[ks], B.q[2 * p + u][ks]);
+                }
+            }
+        };
+        auto epilogue = [&](int p, const double (&c)[2][4]) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int cb = 16 * p + 2 * u;              // first column of n-tile 2 p + u
+                const double f0 = c[u][0] + c[u][2], m0 = c[u][0] - c[u][2];
+                const double f1 = c[u][1] + c[u][3], m1 = c[u][1] - c[u][3];
+                bool l0 = true, l1 = true;
+                if (p < 2) {                                // columns < 32 < Lh: always live
+                    of[cb] = f0; om[-cb] = m0; of[cb + 1] = f1; om[-cb - 1] = m1;
+                } else {                                    // dead columns go to the per-lane sink slot
+                    l0 = (G.live >> (2 * (2 * p + u - 4))) & 1u;
+                    l1 = (G.live >> (2 * (2 * p + u - 4) + 1)) & 1u;
+                    *(l0 ? of + cb : sink) = f0;
+                    *(l0 ? om - cb : sink) = m0;
+                    *(l1 ? of + cb + 1 : sink) = f1;
+                    *(l1 ? om - cb - 1 : sink) = m1;
+                }
+                if (MINMODE == 1) {                         // min(se+so, se-so) = se - |so|, one DADD
+                    mn = dmin(mn, l0 ? c[u][0] - fabs(c[u][2]) : INFINITY);
+                    mn = dmin(mn, l1 ? c[u][1] - fabs(c[u][3]) : INFINITY);
+                } else if (MINMODE == 2) {                  // compare on the integer pipe (order keys)
+                    const long long k0 = order_key(c[u][0] - fabs(c[u][2]));
+                    const long long k1 = order_key(c[u][1] - fabs(c[u][3]));
+                    mk = (l0 && k0 < mk) ? k0 : mk;
+                    mk = (l1 && k1 < mk) ? k1 : mk;
+                }
+            }
+        };
+
+        mma_pair(0, C[0]);
+        // the bulk read of this staging buffer (issued two m-tiles ago) must be done
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (p < 3) mma_pair(p + 1, C[(p + 1) & 1]);
+            else if (mi < 3) {                              // A fragments of the next m-tile
+                const double *an = ar + (size_t)8 * (mi + 1) * kRowStride;
+#pragma unroll
+                for (int ks = 0; ks < KE; ++ks) aE[ks] = an[ks];
+#pragma unroll
+                for (int ks = 0; ks < KO; ++ks) aO[ks] = an[16 + ks];
+            }
+            epilogue(p, C[p & 1]);
+        }
+        mnv[mi] = mn;
+        mkv[mi] = mk;
+        fence_async_smem();                         // generic-proxy writes -> visible to the TMA read
+        __syncwarp();
+        const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
+        double *dst = outg + (size_t)8 * mi * L;
+        const unsigned bytes = (unsigned)(nrows * L) * 8u;
+        if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
+            if (lane == 0) bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes);
+        } else {                                    // odd row count x odd L or unaligned base
+            for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
+        }
+        if (lane == 0) bulk_commit();               // (possibly empty) group keeps the count in step
+    }
+    // per-item minima: reduce over the 4 lanes of a row, then lane (g,t) stores item 8 t + g
+    if (MINMODE == 1) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            mnv[mi] = dmin(mnv[mi], __shfl_xor_sync(0xffffffffu, mnv[mi], 1));
+            mnv[mi] = dmin(mnv[mi], __shfl_xor_sync(0xffffffffu, mnv[mi], 2));
+        }
+        const double v = t == 0 ? mnv[0] : t == 1 ? mnv[1] : t == 2 ? mnv[2] : mnv[3];
+        if (8 * t + g < cnt) ming[8 * t + g] = v;
+    } else if (MINMODE == 2) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            long long o = __shfl_xor_sync(0xffffffffu, mkv[mi], 1);
+            mkv[mi] = o < mkv[mi] ? o : mkv[mi];
+            o = __shfl_xor_sync(0xffffffffu, mkv[mi], 2);
+            mkv[mi] = o < mkv[mi] ? o : mkv[mi];
+        }
+        const long long v = t == 0 ? mkv[0] : t == 1 ? mkv[1] : t == 2 ? mkv[2] : mkv[3];
+        if (8 * t + g < cnt) ming[8 * t + g] = __longlong_as_double(order_key_bits(v));
+    }
+}
+
+}  // namespace bezmma
