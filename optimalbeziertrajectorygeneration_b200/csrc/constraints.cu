@@ -255,7 +255,7 @@ extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, i
     A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = d_pairmin;
     A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
-    A.alpha = 1.0; A.beta = -maxSep2; A.dbg = 0;
+    A.alpha = 1.0; A.beta = -maxSep2;
     if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, PAIR, (cudaStream_t)stream);
     return dispatch_degree<PAIR>(plan, A, (cudaStream_t)stream);
 }
@@ -272,7 +272,7 @@ extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, con
     A.cpts = d_cpts; A.tf = d_tf; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = nullptr;
     A.item_begin = veh_begin; A.nitems = nveh; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
-    A.alpha = alpha; A.beta = beta; A.dbg = 0;
+    A.alpha = alpha; A.beta = beta;
     if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, SPEED, (cudaStream_t)stream);
     return dispatch_degree<SPEED>(plan, A, (cudaStream_t)stream);
 }

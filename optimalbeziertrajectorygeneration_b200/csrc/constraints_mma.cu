@@ -12,83 +12,82 @@ using namespace bezcore;
 // Tensor-path variant (DMMA stage 2 + TMA bulk-store epilogue, sq_elev_mma.cuh) for
 // the shapes of the headline workload: 33..64 column pairs (65 <= L <= 128), n <= 15.
 // Same tiling (one warp = 32 items, no block-wide barriers in the main loop), same
-// stage 1.  Shared memory: B fragments (8 KT x 256 B) | per warp 8.4 KB of staged rows
-// + one [8][L] output staging buffer + 256 B sink.
+// stage 1; per warp 8.4 KB of staged rows + two [8][L] output staging buffers.
 template <int N_, int DIM, int MODE, int MINMODE>
-__global__ void __launch_bounds__(bezmma::kMmaThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N_> DW) {
     using namespace bezmma;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *btab = smem;
-    const size_t per_warp = (size_t)kRowsDoubles + 8 * (size_t)A.L + 32;
-    double *rows = smem + 8 * Geom<N_>::KT * 32 + warp * per_warp;
+    const size_t per_warp = (size_t)kRowsDoubles + 16 * (size_t)A.L + 32;
+    double *rows = smem + warp * per_warp;
     double *obuf = rows + kRowsDoubles;
-    fill_btab<N_>(btab, A.PQ, A.Lh, A.LhPad, tid, kMmaThreads);
     for (int i = lane; i < kRowsDoubles; i += 32) rows[i] = 0.0;     // padding slots must be 0
     const unsigned obuf_s = (unsigned)__cvta_generic_to_shared(obuf);
     const LaneGeom G = lane_geom(lane, A.Lh);
-    __syncthreads();
+    BFrags<N_> Bf;
+    load_bfrags<N_>(Bf, A.PQ, A.Lh, A.LhPad, lane);
+    __syncwarp();
 
     const long long wtiles_per_eval = (A.nitems + 31) >> 5;
     const long long nwt = wtiles_per_eval * A.B;
-    const long long gwarp = (long long)blockIdx.x * kMmaWarps + warp;
-    const long long nwarps = (long long)gridDim.x * kMmaWarps;
-    const double scale = A.alpha * (0.5 * (double)DIM);       // Q1: dim/2 (sign of alpha folded in)
+    const long long gwarp = (long long)blockIdx.x * kWarps + warp;
+    const long long nwarps = (long long)gridDim.x * kWarps;
+    unsigned seq = 0;
 
     for (long long wt = gwarp; wt < nwt; wt += nwarps) {
         const int b = (int)(wt / wtiles_per_eval);
         const long long t0 = (wt - (long long)b * wtiles_per_eval) << 5;
         const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
-        if (!(A.dbg & 1) || wt == gwarp) {
+        {
             double s[2 * N_ + 1];
             stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, t0, lane < cnt ? lane : cnt - 1, s);
             double *row = rows + lane * kRowStride;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
-                const double lo = s[j] * scale, hi = s[2 * N_ - j] * scale;
-                row[slot_e(j)] = lo + hi;
-                row[slot_o(j)] = lo - hi;
+                row[slot_e(j)] = s[j] + s[2 * N_ - j];
+                row[slot_o(j)] = s[j] - s[2 * N_ - j];
             }
-            row[slot_e(N_)] = s[N_] * scale;
+            row[slot_e(N_)] = s[N_];
         }
         __syncwarp();
         const size_t item0 = (size_t)b * A.nitems + t0;
-        mma_tile<N_, MINMODE>(rows, obuf, obuf_s, btab, G, A.out + item0 * A.L,
-                              MINMODE ? A.itemmin + item0 : nullptr, cnt, A.L, A.Lh, A.beta, lane, A.dbg);
+        mma_tile<N_, MINMODE>(rows, obuf, obuf_s, Bf, G, A.out + item0 * A.L, MINMODE ? A.itemmin + item0 : nullptr,
+                               cnt, A.L, A.Lh, A.beta, lane, seq);
         __syncwarp();
     }
-    if (lane == 0) bulk_wait_all();      // the staging buffer must outlive the last bulk read
+    if (lane == 0) bulk_wait_all();      // staging buffers must outlive the last bulk reads
 }
 
 template <int N_, int DIM, int MODE, int MINMODE>
 int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
-    using namespace bezmma;
     ProdWeights<N_> PW;
     DiffWeights<N_> DW;
-    for (int i = 0; i <= N_; ++i)
+    const double scale = A.alpha * (0.5 * (double)DIM);       // Q1: dim/2 and the sign of alpha, folded
+    for (int i = 0; i <= N_; ++i)                             // into the product weights
         for (int j = i; j <= N_; ++j) {
-            double w = plan->h_W[i * (N_ + 1) + j];
+            double w = plan->h_W[i * (N_ + 1) + j] * scale;
             PW.w[widx<N_>(i, j)] = (i == j) ? w : 2.0 * w;
         }
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
-    const size_t shmem = ((size_t)8 * Geom<N_>::KT * 32 +
-                          (size_t)kMmaWarps * (kRowsDoubles + 8 * (size_t)A.L + 32)) * sizeof(double);
+    const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L + 32) * sizeof(double);
     auto kern = sq_elev_mma_kernel<N_, DIM, MODE, MINMODE>;
     static size_t attr_set = 0;
     if (shmem > attr_set) {
         BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
         attr_set = shmem;
     }
-    int dev = 0, sms = 148;
+    int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
+    if (per_sm < 1) per_sm = 1;
     const long long nwt = ((A.nitems + 31) / 32) * A.B;
-    long long grid = sms;                                   // persistent: one CTA per SM
-    const long long need = (nwt + kMmaWarps - 1) / kMmaWarps;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (nwt + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
     if (grid < 1) return BEZ_OK;
-    kern<<<(unsigned)grid, kMmaThreads, shmem, st>>>(A, PW, DW);
+    kern<<<(unsigned)grid, kThreads, shmem, st>>>(A, PW, DW);
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;
 }
@@ -138,9 +137,7 @@ bool bez_sq_elev_mma_supported(const bez_plan *plan) {
     return plan->n <= 15 && plan->Lh > 32 && plan->Lh <= 64 && !bez_force_dfma();
 }
 
-int bez_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A0, int mode, cudaStream_t st) {
-    SqElevArgs A = A0;
-    { const char *e = getenv("BEZGPU_DBG"); A.dbg = e ? atoi(e) : 0; }
+int bez_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, int mode, cudaStream_t st) {
     return mode == PAIR ? mma_dispatch_degree<PAIR>(plan, A, st) : mma_dispatch_degree<SPEED>(plan, A, st);
 }
 

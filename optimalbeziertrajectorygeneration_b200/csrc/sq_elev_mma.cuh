@@ -36,7 +36,6 @@ __host__ __device__ constexpr int slot_o(int j) { return 16 + slot_e(j); }
 template <int N_> struct Geom {
     static constexpr int KE = (N_ + 1 + 3) / 4;    // k-steps over e_0..e_n
     static constexpr int KO = (N_ + 3) / 4;        // k-steps over o_0..o_{n-1}
-    static constexpr int KT = KE + KO;             // B fragments per n-tile
     static_assert(KE <= 4, "slot_e needs 4 ks + t < 16: degree <= 15");
 };
 
@@ -66,31 +65,31 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One CTA = kMmaWarps warps, one CTA per SM (persistent): 3 warps per scheduler hide the
-// stage-1 load latency and the epilogue/bulk-store tails behind the other warps' DMMAs
-// (with 2 warps per scheduler the fp64 pipe idled 46 % of the time).  168 registers per
-// thread do not hold the 8 x KT B fragments, so they live in shared memory in fragment
-// order and are streamed per n-tile pair (lane-contiguous LDS.64, conflict free).
-constexpr int kMmaWarps = 12;
-constexpr int kMmaThreads = 32 * kMmaWarps;
+// Folded elevation weights in B-fragment order, register resident for the whole kernel.
+template <int N_> struct BFrags {
+    double p[8][Geom<N_>::KE];
+    double q[8][Geom<N_>::KO > 0 ? Geom<N_>::KO : 1];
+};
 
-// Folded elevation weights in B-fragment order: fragment (ni, k) of lane l at
-// btab[(ni * KT + k) * 32 + l]; k < KE: P rows 4 k .. 4 k + 3, k >= KE: Q rows 4 (k - KE) ..
 template <int N_>
-__device__ __forceinline__ void fill_btab(double *btab, const double *__restrict__ PQ, int Lh, int LhPad,
-                                          int tid, int nthreads) {
-    constexpr int NC = N_ + 1, KE = Geom<N_>::KE, KT = Geom<N_>::KT;
-    for (int e = tid; e < 8 * KT * 32; e += nthreads) {
-        const int lane = e & 31, f = e >> 5;
-        const int ni = f / KT, k = f - ni * KT;
-        const int g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void load_bfrags(BFrags<N_> &B, const double *__restrict__ PQ, int Lh, int LhPad,
+                                            int lane) {
+    constexpr int NC = N_ + 1;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
         const int col = col_of(ni, g);
-        const bool is_p = k < KE;
-        const int j = 4 * (is_p ? k : k - KE) + t;             // folded row index inside P / Q
-        const bool live = col < Lh && (is_p ? j <= N_ : j < N_);
-        const int row = is_p ? j : NC + j;                      // row of the [2n+1][LhPad] table
-        const double v = live ? __ldg(PQ + (size_t)row * LhPad + col) : 0.0;
-        btab[e] = v;
+        const bool live = col < Lh;
+#pragma unroll
+        for (int ks = 0; ks < Geom<N_>::KE; ++ks) {
+            const int j = 4 * ks + t;
+            B.p[ni][ks] = (live && j <= N_) ? __ldg(PQ + (size_t)j * LhPad + col) : 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < Geom<N_>::KO; ++ks) {
+            const int j = 4 * ks + t;
+            B.q[ni][ks] = (live && j < N_) ? __ldg(PQ + (size_t)(NC + j) * LhPad + col) : 0.0;
+        }
     }
 }
 
@@ -112,31 +111,30 @@ __device__ __forceinline__ LaneGeom lane_geom(int lane, int Lh) {
     return G;
 }
 
-// One warp tile: rows = staged (e,o) rows of 32 items, obuf = [8][L] doubles of staging
-// (+ 32 doubles of sink for dead columns), obuf_s = its shared-window address, btab =
-// B fragments (fill_btab), outg = global address of the tile's first output row (rows
-// contiguous, pitch L), ming = per-item minimum (MINMODE != 0).
+// One warp tile: rows = staged (e,o) rows of 32 items, obuf = 2 x [8][L] doubles of
+// staging (+ 32 doubles of sink for dead columns), obuf_s = its shared-window address,
+// outg = global address of the tile's first output row (rows contiguous, pitch L),
+// ming = per-item minimum (MINMODE != 0).  seq counts m-tiles over the kernel's
+// lifetime and selects the staging buffer (at most one bulk read is left pending).
 //
 // Schedule of one m-tile (8 items): the n-tiles are processed in pairs; the 12 DMMAs of
 // pair p+1 (4 independent accumulator chains, round-robin over the k-steps) are issued
 // before the epilogue of pair p, so the fp64 pipe always has independent work queued
-// behind the DADD/STS of the epilogue.
+// behind the DADD/STS of the epilogue (in-order issue: without this the epilogue waits
+// out the full DMMA latency, 38 % "wait" stalls in profiles/r01_ncu_pair_kernel_mma_v1).
 template <int N_, int MINMODE>
 __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
-                                         const double *btab, const LaneGeom &G,
+                                         const BFrags<N_> &B, const LaneGeom &G,
                                          double *__restrict__ outg, double *__restrict__ ming, int cnt,
-                                         int L, int Lh, double beta, int lane, int dbg = 0) {
-    constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO, KT = Geom<N_>::KT;
+                                         int L, int Lh, double beta, int lane, unsigned &seq) {
+    constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO;
     const int g = G.g, t = G.t;
     const int M = L - 1;
     double mnv[4];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) mnv[mi] = INFINITY;
-    double *const sink = obuf + 8 * L + lane;
-    double *const of = obuf + g * L + 4 * t;       // forward cursor of this lane (column 4 t of row g)
-    double *const om = obuf + g * L + M - 4 * t;   // mirror cursor
+    double *const sink = obuf + 16 * L + lane;
     const double *ar = rows + g * kRowStride + 4 * t;
-    const double *bl = btab + lane;
     double aE[KE], aO[KO > 0 ? KO : 1];
 #pragma unroll
     for (int ks = 0; ks < KE; ++ks) aE[ks] = ar[ks];
@@ -146,33 +144,28 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         if (8 * mi >= cnt) break;
-        double mn = INFINITY;
-        double C[2][2][4], Bp[2][2][KT];
-        auto load_b = [&](int p, double (&b)[2][KT]) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int k = 0; k < KT; ++k) b[u][k] = bl[((2 * p + u) * KT + k) * 32];
-        };
-        auto mma_pair = [&](const double (&b)[2][KT], double (&c)[2][4]) {
+        const unsigned par = seq & 1u;
+        ++seq;
+        double *ob = obuf + (size_t)par * 8 * L;
+        double *of = ob + g * L + 4 * t;           // forward cursor of this lane (column 4 t of row g)
+        double *om = ob + g * L + M - 4 * t;       // mirror cursor
+        double mnp[4];                              // one minimum per n-tile pair: short dependency chains
+        double C[2][2][4];
+        auto mma_pair = [&](int p, double (&c)[2][4]) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) { c[u][0] = beta; c[u][1] = beta; c[u][2] = 0.0; c[u][3] = 0.0; }
-            if (dbg & 2) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) { c[u][0] += b[u][0] + aE[0]; c[u][2] += b[u][KE] + aO[0]; }
-                return;
-            }
 #pragma unroll
             for (int ks = 0; ks < KE; ++ks) {
 #pragma unroll
-                for (int u = 0; u < 2; ++u) dmma884(c[u][0], c[u][1], aE[ks], b[u][ks]);
+                for (int u = 0; u < 2; ++u) dmma884(c[u][0], c[u][1], aE[ks], B.p[2 * p + u][ks]);
                 if (ks < KO) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) dmma884(c[u][2], c[u][3], aO[ks], b[u][KE + ks]);
+                    for (int u = 0; u < 2; ++u) dmma884(c[u][2], c[u][3], aO[ks], B.q[2 * p + u][ks]);
                 }
             }
         };
         auto epilogue = [&](int p, const double (&c)[2][4]) {
+            double cand[2][2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int cb = 16 * p + 2 * u;              // first column of n-tile 2 p + u
@@ -190,23 +183,21 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
                     *(l1 ? om - cb - 1 : sink) = m1;
                 }
                 if (MINMODE) {                              // min(se+so, se-so) = se - |so|, one DADD
-                    mn = dmin(mn, l0 ? c[u][0] - fabs(c[u][2]) : INFINITY);
-                    mn = dmin(mn, l1 ? c[u][1] - fabs(c[u][3]) : INFINITY);
+                    cand[u][0] = l0 ? c[u][0] - fabs(c[u][2]) : INFINITY;
+                    cand[u][1] = l1 ? c[u][1] - fabs(c[u][3]) : INFINITY;
                 }
             }
+            if (MINMODE) mnp[p] = dmin(dmin(cand[0][0], cand[0][1]), dmin(cand[1][0], cand[1][1]));
         };
 
-        load_b(0, Bp[0]);
-        mma_pair(Bp[0], C[0]);
-        // the bulk read of the staging buffer (previous m-tile) must be done before it is rewritten
-        if (lane == 0) bulk_wait_read<0>();
+        mma_pair(0, C[0]);
+        // the bulk read of this staging buffer (issued two m-tiles ago) must be done
+        if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            if (p < 3) {
-                load_b(p + 1, Bp[(p + 1) & 1]);
-                mma_pair(Bp[(p + 1) & 1], C[(p + 1) & 1]);
-            } else if (mi < 3) {                            // A fragments of the next m-tile
+            if (p < 3) mma_pair(p + 1, C[(p + 1) & 1]);
+            else if (mi < 3) {                              // A fragments of the next m-tile
                 const double *an = ar + (size_t)8 * (mi + 1) * kRowStride;
 #pragma unroll
                 for (int ks = 0; ks < KE; ++ks) aE[ks] = an[ks];
@@ -215,17 +206,18 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
             }
             epilogue(p, C[p & 1]);
         }
-        mnv[mi] = mn;
+        if (MINMODE) mnv[mi] = dmin(dmin(mnp[0], mnp[1]), dmin(mnp[2], mnp[3]));
         fence_async_smem();                         // generic-proxy writes -> visible to the TMA read
         __syncwarp();
         const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
         double *dst = outg + (size_t)8 * mi * L;
         const unsigned bytes = (unsigned)(nrows * L) * 8u;
         if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
-            if (lane == 0 && !(dbg & 4)) { bulk_store(dst, obuf_s, bytes); bulk_commit(); }
+            if (lane == 0) bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes);
         } else {                                    // odd row count x odd L or unaligned base
-            for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, obuf[i]);
+            for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
         }
+        if (lane == 0) bulk_commit();               // (possibly empty) group keeps the count in step
     }
     // per-item minima: reduce over the 4 lanes of a row, then lane (g,t) stores item 8 t + g
     if (MINMODE) {

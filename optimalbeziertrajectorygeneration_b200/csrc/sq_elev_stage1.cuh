@@ -17,7 +17,6 @@ struct SqElevArgs {
     long long nitems;       // pairs / vehicles per evaluation point
     int B, N, L, Lh, LhPad;
     double alpha, beta;     // out = alpha * value + beta   (alpha = +-1)
-    int dbg;                // development ablation bits (BEZGPU_DBG), 0 in production
 };
 
 // Stage 1 for one item (lane = item): the 2n+1 Bernstein coefficients (before the
