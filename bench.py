@@ -319,6 +319,13 @@ def run_ours(opts):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg_bytes = 8.0 * B * (P * L + P + 34 * N)      # rows + per-pair minima written, control-point rows read
         achieved = alg_bytes / (kms * 1e-3) / 1e9
+        # measured DRAM traffic of the same launch shape from the committed ncu --set full capture
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("evals_per_launch") == B:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         evals = B * world * opts.steps
         line = {"metric": "constraint+Jacobian evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s",
                 "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
@@ -326,7 +333,8 @@ def run_ours(opts):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(B),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "kernel": "sq_elev_kernel<10,3,PAIR,2,min>",
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "kernel": "sq_elev_mma_kernel<10,3,PAIR,min> (DMMA.8x8x4 stage 2, TMA bulk-store epilogue)",
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": launches_per_step * opts.steps, "clocks": clocks}
         if world == 1 and not opts.no_cpu:

@@ -123,11 +123,11 @@ int mma_dispatch_degree(const bez_plan *plan, const SqElevArgs &A, cudaStream_t 
 
 namespace bezcore {
 
-// BEZGPU_FORCE_DFMA=1 keeps every shape on the column-stationary DFMA kernel (A/B runs).
+// BEZGPU_FORCE_DFMA=1 keeps every shape on the column-stationary DFMA kernel (A/B runs and
+// tests/test_gpu_constraints.py::test_tensor_path_matches_dfma_path); read on every call.
 static bool bez_force_dfma() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("BEZGPU_FORCE_DFMA"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
+    const char *e = getenv("BEZGPU_FORCE_DFMA");
+    return e && e[0] == '1';
 }
 
 bool bez_sq_elev_mma_supported(const bez_plan *plan) {

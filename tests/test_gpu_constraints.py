@@ -81,7 +81,10 @@ def test_c5_like_golden(gopt, golden):
 
 
 @pytest.mark.parametrize("dim,deg,N,E", [(1, 3, 5, 0), (2, 1, 4, 3), (3, 7, 9, 21), (2, 12, 7, 64),
-                                         (3, 16, 5, 40), (3, 10, 40, 300), (2, 4, 300, 1)])
+                                         (3, 16, 5, 40), (3, 10, 40, 300), (2, 4, 300, 1),
+                                         # 33..64 column pairs: the fp64 tensor-path kernels (DMMA + TMA stores)
+                                         (3, 10, 40, 100), (2, 5, 33, 60), (1, 15, 20, 97), (3, 4, 37, 56),
+                                         (2, 10, 12, 43), (3, 10, 9, 44), (2, 8, 11, 75), (3, 13, 70, 101)])
 def test_random_models_vs_oracle(gopt, dim, deg, N, E):
     from oracle import bezier_oracle as O
     rng = np.random.default_rng(deg * 100 + N)
@@ -122,6 +125,86 @@ def test_batched_and_pair_ranges(gopt):
     pm = torch.empty((5, P), dtype=torch.float64, device=full.device)
     eng.separation(cpts, 100, 0.9, pairmin=pm)
     assert torch.equal(pm, full.min(dim=2).values)
+
+
+def test_tensor_path_matches_dfma_path(gopt, monkeypatch):
+    """The DMMA/TMA kernels and the column-stationary DFMA kernels are two evaluations of
+    the same folded sums: values agree to rounding, per-pair minima follow their values."""
+    import torch
+    from oracle.make_golden import synthetic_swarm_args
+    args, x = synthetic_swarm_args(70)
+    b = gopt.BezOptimization(**args)
+    X = x[None, :] + np.random.default_rng(3).normal(size=(3, x.size)) * 0.05
+    eng = b._engine(True)
+    cpts, tf = eng.assemble(eng.upload(X), 100)
+    outs = {}
+    for force in ("0", "1"):
+        monkeypatch.setenv("BEZGPU_FORCE_DFMA", force)
+        sep = eng.separation(cpts, 100, 0.9)
+        pm = torch.empty(sep.shape[:2], dtype=torch.float64, device=sep.device)
+        eng.separation(cpts, 100, 0.9, pairmin=pm)
+        spd = eng.speed(cpts, tf, 100, -1.0, 25.0)
+        assert torch.equal(pm, sep.min(dim=2).values)
+        outs[force] = (sep.cpu().numpy(), spd.cpu().numpy())
+    assert relerr(outs["0"][0], outs["1"][0]) < 1e-13
+    assert relerr(outs["0"][1], outs["1"][1]) < 1e-13
+    assert not np.array_equal(outs["0"][0], outs["1"][0])     # really two different kernels
+
+
+def test_c4_full_size_properties(gopt):
+    """BASELINE configs[3] at full size (1024 vehicles, 523 776 pairs x 121 values): sampled
+    pair blocks against the C oracle, and size-independent properties over every pair --
+    end-point identity of degree elevation (b_0 = s_0, b_M = s_2n), invariance of the
+    coefficient mean under elevation, fused per-pair minimum == row minimum, FD-perturbed
+    x changes exactly the rows of the perturbed vehicle."""
+    import torch
+    from oracle import bezier_oracle as O
+    from oracle import c_oracle as C
+    from oracle.make_golden import synthetic_swarm_args
+    N, E, n = 1024, 100, 10
+    args, x = synthetic_swarm_args(N)
+    b = gopt.BezOptimization(**args)
+    eng = b._engine(True)
+    X = np.stack([x, x])
+    k = 3 * 9 * 500 + 4                      # a free control point of vehicle 500
+    X[1, k] += 1.4901161193847656e-08
+    cpts, tf = eng.assemble(eng.upload(X), E)
+    P = N * (N - 1) // 2
+    L = 2 * n + E + 1
+    sep = torch.empty((2, P, L), dtype=torch.float64, device=eng.device)
+    pm = torch.empty((2, P), dtype=torch.float64, device=eng.device)
+    eng.separation(cpts, E, args["maxSep"], out=sep, pairmin=pm)
+    y = O.reshape_vector(O.Model(**args), x)
+    # (1) sampled contiguous pair blocks vs the C restatement of the reference
+    for begin in (0, 1023, 77777, 261888, P - 4096):
+        want = C.temporal_separation(y, N, 3, args["maxSep"], E, begin, 4096).reshape(4096, L)
+        got = sep[0, begin:begin + 4096].cpu().numpy()
+        assert relerr(got, want) < RTOL
+    # (2) fused minimum is the row minimum, bit for bit, for all 2 x 523 776 pairs
+    assert torch.equal(pm, sep.min(dim=2).values)
+    # (3) end points and mean over all pairs (vectorised numpy restatement of sub -> normSquare)
+    c = y.reshape(N, 3, n + 1)
+    iu, ju = np.triu_indices(N, 1)
+    d0 = c[iu, :, 0] - c[ju, :, 0]
+    dn = c[iu, :, n] - c[ju, :, n]
+    s0 = 1.5 * (d0 * d0).sum(axis=1) - args["maxSep"] ** 2
+    sn = 1.5 * (dn * dn).sum(axis=1) - args["maxSep"] ** 2
+    got0 = sep[0, :, 0].cpu().numpy()
+    gotn = sep[0, :, L - 1].cpu().numpy()
+    assert np.abs(got0 - s0).max() / np.abs(s0).max() < 1e-12
+    assert np.abs(gotn - sn).max() / np.abs(sn).max() < 1e-12
+    W = O.prod_weights(n)
+    a = c[iu[:20000]] - c[ju[:20000]]                       # [pairs, 3, n+1]
+    G = np.einsum('pdi,pdj->pij', a, a) * W
+    smean = np.array([np.trace(G[:, ::-1], offset=n - kk, axis1=1, axis2=2) for kk in range(2 * n + 1)]).T
+    smean = 1.5 * smean.mean(axis=1) - args["maxSep"] ** 2    # mean of the 2n+1 product coefficients
+    gotmean = sep[0, :20000].mean(dim=1).cpu().numpy()
+    assert np.abs(gotmean - smean).max() / np.abs(smean).max() < 1e-12
+    # (4) the perturbed evaluation differs from the base one only in pairs that contain vehicle 500
+    changed = (sep[0] != sep[1]).any(dim=1).cpu().numpy()
+    touches = (iu == 500) | (ju == 500)
+    assert not changed[~touches].any()
+    assert changed[touches].mean() > 0.5
 
 
 def test_single_vehicle_returns_none(gopt):
