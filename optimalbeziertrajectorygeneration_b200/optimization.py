@@ -339,6 +339,65 @@ class BezOptimization:
             pmh, sph = pmh.copy(), sph.copy()
         return {'pairmin': pmh, 'maxspeed': sph}
 
+    def evaluate_sweep(self, X, elev=None, chunk=4, out=None):
+        """Pipelined form of :meth:`evaluate_reduced` for the nvar+1 points of a finite
+        difference sweep (SciPy asks for them one by one, `_numdiff.py:683-712`; here the
+        caller hands all of them over): host X [M, nvar] is processed in chunks of
+        ``chunk`` rows with two device workspaces, so that the pinned host->device copy
+        and the kernels of chunk k+1 overlap the device->host copy of chunk k (separate
+        copy stream, events, no host synchronisation inside the loop).  Returns host
+        arrays ``pairmin`` [M, P] and ``maxspeed`` [M, numVeh*L] (pinned; reused by the
+        next call unless ``out`` supplies the destination dict of pinned tensors)."""
+        E = _deg_elev() if elev is None else int(elev)
+        eng = self._engine(with_obstacles=True)
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        M = X.shape[0]
+        if X.shape[1] != eng.nvar:
+            raise ValueError("x has %d entries, the model expects %d" % (X.shape[1], eng.nvar))
+        P = _engine.num_pairs(eng.N)
+        L = 2 * self.model['deg'] + E + 1
+        nv = self.model['numVeh']
+        chunk = max(1, min(int(chunk), M))
+        sw = getattr(self, '_sweep_ws', None)
+        if sw is None or sw['key'] != (chunk, E):
+            def wsset():
+                return {'x': torch.empty((chunk, eng.nvar), dtype=torch.float64, device=eng.device),
+                        'sep': torch.empty((chunk, P, L), dtype=torch.float64, device=eng.device),
+                        'pairmin': torch.empty((chunk, P), dtype=torch.float64, device=eng.device),
+                        'maxspeed': torch.empty((chunk, nv, L), dtype=torch.float64, device=eng.device),
+                        'done': None}
+            sw = {'key': (chunk, E), 'sets': [wsset(), wsset()], 'copy_stream': torch.cuda.Stream(device=eng.device)}
+            self._sweep_ws = sw
+        if out is None:
+            out = {'pairmin': eng._pinned_buf('sweep_pairmin', M * P).view(M, P),
+                   'maxspeed': eng._pinned_buf('sweep_maxspeed', M * nv * L).view(M, nv * L)}
+        xs = eng._pinned_buf('sweep_x', X.size).view(M, eng.nvar)
+        xs.numpy()[:] = X
+        main, side = torch.cuda.current_stream(), sw['copy_stream']
+        max_speed2 = float(self.model['maxSpeed']) ** 2
+        for k, lo in enumerate(range(0, M, chunk)):
+            hi = min(M, lo + chunk)
+            b = hi - lo
+            ws = sw['sets'][k & 1]
+            if ws['done'] is not None:
+                main.wait_event(ws['done'])          # D2H of the chunk that used this set two steps ago
+            ws['x'][:b].copy_(xs[lo:hi], non_blocking=True)
+            cpts, tf = eng.assemble(ws['x'][:b], E)
+            eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b], pairmin=ws['pairmin'][:b])
+            eng.speed(cpts, tf, E, -1.0, max_speed2, nveh=nv, out=ws['maxspeed'][:b])
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                out['pairmin'][lo:hi].copy_(ws['pairmin'][:b], non_blocking=True)
+                out['maxspeed'][lo:hi].copy_(ws['maxspeed'][:b].view(b, -1), non_blocking=True)
+                ws['done'] = torch.cuda.Event()
+                ws['done'].record(side)
+        side.synchronize()
+        main.synchronize()
+        self.workspace = {'key': None, 'sep': sw['sets'][(k & 1)]['sep']}
+        return {'pairmin': out['pairmin'].numpy(), 'maxspeed': out['maxspeed'].numpy()}
+
     # -- cost callables (A14, optimization.py:287-308) -----------------------
     def _objective(self, x, kind):
         eng = self._engine(with_obstacles=False)

@@ -207,6 +207,23 @@ def test_c4_full_size_properties(gopt):
     assert changed[touches].mean() > 0.5
 
 
+def test_evaluate_sweep_matches_serial_calls(gopt):
+    """The pipelined sweep (two workspaces, copy stream) returns what per-chunk
+    evaluate_reduced calls return, including a ragged last chunk."""
+    from oracle.make_golden import synthetic_swarm_args
+    args, x = synthetic_swarm_args(40)
+    b = gopt.BezOptimization(**args)
+    X = x[None, :] + np.random.default_rng(5).normal(size=(11, x.size)) * 0.02
+    sw = b.evaluate_sweep(X, elev=100, chunk=4)
+    pm, sp = sw["pairmin"].copy(), sw["maxspeed"].copy()
+    for lo in range(0, 11, 4):
+        red = b.evaluate_reduced(X[lo:lo + 4], elev=100)
+        assert np.array_equal(pm[lo:lo + 4], red["pairmin"])
+        assert np.array_equal(sp[lo:lo + 4], red["maxspeed"])
+    sw2 = b.evaluate_sweep(X[:3], elev=100, chunk=8)          # fewer rows than the chunk
+    assert np.array_equal(sw2["pairmin"], pm[:3])
+
+
 def test_single_vehicle_returns_none(gopt):
     b = gopt.BezOptimization(numVeh=1, dimension=2, degree=5, initPoints=[(0, 0)], finalPoints=[(1, 1)])
     assert b.temporalSeparationConstraints(np.zeros(b.nvar)) is None
