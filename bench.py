@@ -328,6 +328,29 @@ def run_ours(opts):
                                    "508 MB constraint vector to host memory (PCIe-bound)"}}
     gopt.DEG_ELEV = 0
 
+    # Sparse-aware FD sweep: the whole Jacobian of the separation block of ONE x
+    # (what SLSQP obtains from nvar+1 = 27 649 full evals) in closed form, sweep layout
+    # [variable][partner curve][L] = only the rows that depend on the variable (27.4 GB).
+    sweep = None
+    if not opts.no_sweep:
+        torch.cuda.empty_cache()
+        J = eng.jac_separation(x, E, dense=False)
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(3):
+            J = eng.jac_separation(x, E, dense=False)
+        b_.record()
+        torch.cuda.synchronize()
+        sms = a_.elapsed_time(b_) / 3
+        sweep = {"value": (bezopt.nvar + 1) * world / (sms * 1e-3), "unit": "evals/s",
+                 "ms_per_jacobian": sms, "bytes_per_jacobian": int(J.numel() * 8),
+                 "note": "closed-form FD Jacobian of the separation block of one x (all %d variables x %d partner "
+                         "curves x %d values), equivalent to nvar+1 full evals of the reference; every rank "
+                         "computes the Jacobian of its own x" % (bezopt.nvar, N - 1, L)}
+        del J
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -355,9 +378,115 @@ def run_ours(opts):
                              "kernel": "sq_elev_mma_kernel<10,3,PAIR,min> (DMMA.8x8x4 stage 2, TMA bulk-store epilogue)",
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": launches_per_step * opts.steps, "clocks": clocks}
+        if sweep is not None:
+            sweep["hbm_frac"] = sweep["bytes_per_jacobian"] / (sweep["ms_per_jacobian"] * 1e-3) / 1e9 / peak
+            line["jacobian_sweep"] = sweep
         if world == 1 and not opts.no_cpu:
             cb, _ = cpu_baseline(args, x, E, target_seconds=12.0)
             line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------
+def run_c5(opts):
+    """Secondary workload (BASELINE.json configs[4], SURVEY 8(d) "C5"): independent Dubins
+    time-optimal problems (1 vehicle, degree 10, DEG_ELEV 100, 16 point obstacles each);
+    one step = one FD sweep (nvar+1 = 16 evals) of every problem of this rank's block.
+    Problems are dealt out in contiguous blocks (no collective).  Not the headline line:
+    run with `--workload c5`."""
+    import torch
+    import torch.distributed as dist
+    from optimalbeziertrajectorygeneration_b200 import optimization as gopt
+    from optimalbeziertrajectorygeneration_b200 import sharding
+    from optimalbeziertrajectorygeneration_b200.batch import ProblemBatch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Mtot = opts.problems * world                                # weak scaling: problems per rank fixed
+    lo, hi = sharding.block_range(Mtot, world, rank)
+    M, E, nobs, deg = hi - lo, 100, 16, 10
+    template = dict(numVeh=1, dimension=2, degree=deg, minimizeGoal='TimeOpt', maxSep=1, maxSpeed=3,
+                    maxAngRate=np.pi / 2, initPoints=[(0, 0)], finalPoints=[(12, 8)], initSpeeds=[1],
+                    finalSpeeds=[1], tf=8, initAngs=[np.pi / 2], finalAngs=[0])
+    sets = np.stack([np.random.default_rng(p).uniform(1.0, 11.0, size=(nobs, 2)) for p in range(lo, hi)])
+    pb = ProblemBatch(template, sets)
+    guess = gopt.BezOptimization(**template).generateGuess(std=0)
+    X = guess[None, :] + np.stack([np.random.default_rng(10 ** 6 + p).normal(size=guess.size) * 0.5
+                                   for p in range(lo, hi)])
+    X[:, -1] = np.abs(X[:, -1]) + 4.0                            # tf stays positive
+    Xp, dx = pb.fd_points(X)
+    nv1 = pb.nvar + 1
+    d_X = Xp.view(M * nv1, pb.nvar)
+
+    def step():
+        return pb.evaluate(d_X, nv1, elev=E)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, opts.warmup)):
+        F = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(opts.steps):
+        F = step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=pb.eng.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    # per-block kernel times (CUDA events) to name the dominant kernel
+    cpts, tf = pb.eng.assemble(d_X, E, obst_sets=pb.d_obst, evals_per_set=nv1)
+    parts = {}
+    for name, fn in (("separation", lambda: pb.eng.separation(cpts, E, 1.0, pair_begin=0, npairs=pb.npairs_x)),
+                     ("maxspeed", lambda: pb.eng.speed(cpts, tf, E, -1.0, 9.0)),
+                     ("angrate", lambda: pb.eng.angrate(cpts, tf, E, -1.0, (np.pi / 2) ** 2))):
+        fn()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        parts[name] = a.elapsed_time(b_) / 3
+    if rank == 0:
+        L, A = 2 * deg + E + 1, 4 * (deg + E) + 1
+        evals = M * nv1 * world * opts.steps
+        alg_eval = 8.0 * (pb.npairs_x * L + L + A + 2 * (deg + 1) + 1)       # SURVEY 8(d): 20 168 B
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        m_ = deg + E
+        fma_eval = 4 * (m_ + 1) ** 2 + 2 * (2 * m_ + 1) ** 2                    # SURVEY 8(d): 146 966 MAC
+        line = {"metric": "constraint+Jacobian evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s",
+                "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup), "ms_per_step": ms / opts.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C5 synthetic Dubins batch: %d problems per GPU x (nvar+1 = %d) FD points, "
+                                       "1 vehicle + 16 point obstacles, dim 2, degree 10, DEG_ELEV 100: 16 separation "
+                                       "rows + max-speed row + angular-rate row per eval" % (M, nv1),
+                           "problems_per_gpu": M, "sharding": "contiguous blocks of problems per rank, no collective"},
+                "kernel_ms": parts,
+                "roofline": {"bound": "fp64 (angular rate) / hbm (separation rows)",
+                             "hbm_frac_whole_step": alg_eval * M * nv1 / (ms / opts.steps * 1e-3) / 1e9 / peak,
+                             "angrate_fp64_frac": fma_eval * M * nv1 / (parts["angrate"] * 1e-3) / (64 * 148 * 1.965e9),
+                             "separation_hbm_frac": 8.0 * pb.npairs_x * L * M * nv1 / (parts["separation"] * 1e-3) / 1e9 / peak,
+                             "peak": peak, "unit": "GB/s",
+                             "note": "fp64 peak = 64 FMA/clk/SM x 148 SMs x 1.965 GHz (tools/pipe_bench.cu)"},
+                "gpu_launches": 4 * opts.steps, "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -371,9 +500,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="evals (x vectors) per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the closed-form Jacobian sweep leg")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4 = the headline swarm (default); c5 = batch of independent Dubins problems")
+    ap.add_argument("--problems", type=int, default=8192, help="c5: problems per GPU")
     opts = ap.parse_args()
     if opts.impl == "reference":
         run_reference(opts)
+    elif opts.workload == "c5":
+        run_c5(opts)
     else:
         run_ours(opts)
 

@@ -85,6 +85,19 @@ int bez_assemble_cpts(const bez_plan *plan, const double *d_x, int B, int nvar,
                       const double *d_fcos, const double *d_fsin,
                       const double *d_obst,
                       double *d_cpts, double *d_tf, void *stream);
+/* The same for a batch of independent problems that share the model and differ in their
+ * point obstacles (BASELINE.json configs[4]: 65 536 Dubins problems x 16 obstacles x the
+ * nvar+1 points of each problem's FD sweep):  d_obst is [nsets][nObs][dim] and evaluation
+ * b takes set b / evals_per_obst_set (0 = one set for all, i.e. bez_assemble_cpts). */
+int bez_assemble_cpts_sets(const bez_plan *plan, const double *d_x, int B, int nvar,
+                           int numVeh, int nObs, int fixed_ends, int dubins, int timeopt,
+                           double tf_fixed,
+                           const double *d_init, const double *d_final,
+                           const double *d_ispeed, const double *d_fspeed,
+                           const double *d_icos, const double *d_isin,
+                           const double *d_fcos, const double *d_fsin,
+                           const double *d_obst, int evals_per_obst_set,
+                           double *d_cpts, double *d_tf, void *stream);
 
 /* ---- A1-A4: _temporalSeparationConstraints (optimization.py:311-346) =
  * Bezier.sub (bezier.py:347-374) -> normSquare/_normSquare (bezier.py:869-889,
@@ -161,6 +174,9 @@ int bez_jac_speed_sq_elev(const bez_plan *plan, const double *d_cpts, int N, int
  * 0 and f(x0 + h_k e_k) in row k+1; d_JT [nvar][m] = (F[k+1] - F[0]) / dx[k]. */
 int bez_fd_quotient(const double *d_F, const double *d_dx, int nvar, int64_t m,
                     double *d_JT, void *stream);
+/* count independent sweeps: d_F [count][nvar+1][m], d_dx [count][nvar], d_JT [count][nvar][m] */
+int bez_fd_quotient_batched(const double *d_F, const double *d_dx, int64_t count, int nvar,
+                            int64_t m, double *d_JT, void *stream);
 
 /* ---- single-curve algebra behind the bezier.Bezier methods, batched over
  * independent rows/curves; tables are DEVICE arrays the caller built on the host

@@ -40,6 +40,8 @@ SIGNATURES = {
                           ctypes.POINTER(I)]),
     "bez_assemble_cpts": (I, [c_plan_p, P, I, I, I, I, I, I, I, D,
                               P, P, P, P, P, P, P, P, P, P, P, P]),
+    "bez_assemble_cpts_sets": (I, [c_plan_p, P, I, I, I, I, I, I, I, D,
+                                   P, P, P, P, P, P, P, P, P, I, P, P, P]),
     "bez_pair_sepsq_elev": (I, [c_plan_p, P, I, I, L64, L64, D, P, P, P]),
     "bez_speed_sq_elev": (I, [c_plan_p, P, P, I, I, I, I, D, D, P, P]),
     "bez_angrate_tables_create": (I, [I, I, I, P, P, P, P, ctypes.POINTER(c_plan_p)]),
@@ -65,6 +67,7 @@ SIGNATURES = {
     "bez_collcheck2poly_scratch_doubles": (ctypes.c_size_t, [I, I]),
     "bez_collcheck2poly": (I, [P, P, P, I, I, I, I, ctypes.c_longlong, P, P, P, P]),
     "bez_fd_quotient": (I, [P, P, I, L64, P, P]),
+    "bez_fd_quotient_batched": (I, [P, P, L64, I, L64, P, P]),
     "bez_jac_sepsq_elev": (I, [c_plan_p, P, I, I, I, I, P, P, I, I, P, L64, P]),
     "bez_jac_speed_sq_elev": (I, [c_plan_p, P, I, I, I, I, D, D, P, P, I, I, P, L64, P]),
 }

@@ -50,25 +50,27 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
     for (int i = tid; i < NT * A.LhPad; i += kThreads) tab[i] = __ldg(A.PQ + i);
     __syncthreads();
 
-    const long long wtiles_per_eval = (A.nitems + 31) >> 5;
-    const long long nwt = wtiles_per_eval * A.B;
+    // tiles run over the flattened item list [B][nitems] (output rows are contiguous across
+    // evaluation points), so small per-evaluation item counts still fill the warps
+    const long long total = A.nitems * (long long)A.B;
+    const long long nwt = (total + 31) >> 5;
     const long long gwarp = (long long)blockIdx.x * kWarps + (tid >> 5);
     const long long nwarps = (long long)gridDim.x * kWarps;
     const int M = A.L - 1;
-    constexpr int S = (DIM * NC + 1) / 2 * 2;                 // doubles per vehicle row (16 B aligned)
-    const size_t bstride = (size_t)S * A.N;
     const int ngroups = (A.LhPad / 32 + CPL - 1) / CPL;     // sweeps over the columns
     const double scale = A.alpha * (0.5 * (double)DIM);       // Q1: dim/2 (sign of alpha folded in)
 
     for (long long wt = gwarp; wt < nwt; wt += nwarps) {
-        const int b = (int)(wt / wtiles_per_eval);
-        const long long t0 = (wt - (long long)b * wtiles_per_eval) << 5;   // first item of the tile
-        const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
+        const long long g0 = wt << 5;                          // first flattened item of the tile
+        const int cnt = (int)((total - g0) < 32 ? (total - g0) : 32);
 
         // ------------------------- stage 1: lane = item -------------------------
         {
             double s[2 * N_ + 1];
-            stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, t0, lane < cnt ? lane : cnt - 1, s);
+            // lanes past the end recompute the last item so every staged row is finite
+            const long long gi = g0 + (lane < cnt ? lane : cnt - 1);
+            const int b = (int)(gi / A.nitems);
+            stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, gi - (long long)b * A.nitems, 0, s);
             double2 *row = rows + (size_t)lane * RS;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
@@ -80,7 +82,7 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
         __syncwarp();
 
         // ------------------- stage 2: lane = output column(s) -------------------
-        double *outb = A.out + ((size_t)b * A.nitems + t0) * A.L;
+        double *outb = A.out + (size_t)g0 * A.L;
         for (int g = 0; g < ngroups; ++g) {
             if (cnt == 32)
                 sweep_columns<N_, CPL, WITH_MIN, true>(rows, tab, outb, g, lane, 32, A.L, A.Lh, A.LhPad, A.beta);
@@ -97,7 +99,7 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
                 m0 = dmin(m0, mb[q]); m1 = dmin(m1, mb[q + 1]);
                 m2 = dmin(m2, mb[q + 2]); m3 = dmin(m3, mb[q + 3]);
             }
-            if (lane < cnt) A.itemmin[(size_t)b * A.nitems + t0 + lane] = dmin(dmin(m0, m1), dmin(m2, m3));
+            if (lane < cnt) A.itemmin[g0 + lane] = dmin(dmin(m0, m1), dmin(m2, m3));
         }
         __syncwarp();
     }
@@ -108,6 +110,7 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
 struct AssembleArgs {
     const double *x;
     int B, nvar, numVeh, nObs, n, dim, fixed_ends, dubins, timeopt;
+    int evals_per_obst_set;   // > 0: evaluation b uses obstacle set b / evals_per_obst_set
     double tf_fixed;
     const double *init, *fin, *ispeed, *fspeed, *icos, *isin, *fcos, *fsin, *obst;
     double *cpts, *tf;
@@ -132,7 +135,8 @@ __global__ void assemble_cpts_kernel(const AssembleArgs A) {
         const double tf = A.timeopt ? x[A.nvar - 1] : A.tf_fixed;
         double val;
         if (v >= A.numVeh) {
-            val = A.obst[(size_t)(v - A.numVeh) * A.dim + d];            // constant curve (Q8)
+            const size_t set = A.evals_per_obst_set > 0 ? (size_t)(b / A.evals_per_obst_set) : 0;
+            val = A.obst[(set * A.nObs + (v - A.numVeh)) * A.dim + d];    // constant curve (Q8)
         } else if (A.fixed_ends && k == 0) {
             val = A.init[(size_t)v * A.dim + d];
         } else if (A.fixed_ends && k == A.n) {
@@ -183,7 +187,7 @@ int launch_sq_elev2(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
     if (per_sm < 1) per_sm = 1;
-    const long long nwt = ((A.nitems + 31) / 32) * A.B;
+    const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
     long long grid = (long long)sms * per_sm;
     const long long need = (nwt + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
@@ -286,6 +290,21 @@ extern "C" int bez_assemble_cpts(const bez_plan *plan, const double *d_x, int B,
                                  const double *d_fcos, const double *d_fsin,
                                  const double *d_obst,
                                  double *d_cpts, double *d_tf, void *stream) {
+    return bez_assemble_cpts_sets(plan, d_x, B, nvar, numVeh, nObs, fixed_ends, dubins, timeopt, tf_fixed,
+                                  d_init, d_final, d_ispeed, d_fspeed, d_icos, d_isin, d_fcos, d_fsin,
+                                  d_obst, 0, d_cpts, d_tf, stream);
+}
+
+extern "C" int bez_assemble_cpts_sets(const bez_plan *plan, const double *d_x, int B, int nvar,
+                                      int numVeh, int nObs, int fixed_ends, int dubins, int timeopt,
+                                      double tf_fixed,
+                                      const double *d_init, const double *d_final,
+                                      const double *d_ispeed, const double *d_fspeed,
+                                      const double *d_icos, const double *d_isin,
+                                      const double *d_fcos, const double *d_fsin,
+                                      const double *d_obst, int evals_per_obst_set,
+                                      double *d_cpts, double *d_tf, void *stream) {
+    BEZ_REQUIRE(evals_per_obst_set >= 0, "evals_per_obst_set is negative");
     BEZ_REQUIRE(plan && d_cpts && d_tf, "NULL argument");
     BEZ_REQUIRE(d_x || nvar == 0, "x is NULL");
     BEZ_REQUIRE(B >= 0 && numVeh >= 1 && nObs >= 0, "bad sizes");
@@ -305,7 +324,7 @@ extern "C" int bez_assemble_cpts(const bez_plan *plan, const double *d_x, int B,
     A.dim = plan->dim; A.fixed_ends = fixed_ends; A.dubins = dubins; A.timeopt = timeopt;
     A.tf_fixed = tf_fixed; A.init = d_init; A.fin = d_final; A.ispeed = d_ispeed;
     A.fspeed = d_fspeed; A.icos = d_icos; A.isin = d_isin; A.fcos = d_fcos; A.fsin = d_fsin;
-    A.obst = d_obst; A.cpts = d_cpts; A.tf = d_tf;
+    A.obst = d_obst; A.cpts = d_cpts; A.tf = d_tf; A.evals_per_obst_set = evals_per_obst_set;
     const int S = (plan->dim * (plan->n + 1) + 1) / 2 * 2;
     const long long total = (long long)B * (numVeh + nObs) * S;
     long long blocks = (total + 255) / 256;

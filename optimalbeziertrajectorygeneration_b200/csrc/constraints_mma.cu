@@ -29,19 +29,24 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
     load_bfrags<N_>(Bf, A.PQ, A.Lh, A.LhPad, lane);
     __syncwarp();
 
-    const long long wtiles_per_eval = (A.nitems + 31) >> 5;
-    const long long nwt = wtiles_per_eval * A.B;
+    // Tiles run over the flattened item list (evaluation-major, [B][nitems]): the output rows
+    // of consecutive items are contiguous across evaluation points, so a tile may straddle
+    // them (C5 has 16 pair rows / 1 speed row per evaluation).
+    const long long total = A.nitems * (long long)A.B;
+    const long long nwt = (total + 31) >> 5;
     const long long gwarp = (long long)blockIdx.x * kWarps + warp;
     const long long nwarps = (long long)gridDim.x * kWarps;
     unsigned seq = 0;
 
     for (long long wt = gwarp; wt < nwt; wt += nwarps) {
-        const int b = (int)(wt / wtiles_per_eval);
-        const long long t0 = (wt - (long long)b * wtiles_per_eval) << 5;
-        const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
+        const long long g0 = wt << 5;                          // first flattened item of the tile
+        const int cnt = (int)((total - g0) < 32 ? (total - g0) : 32);
         {
+            // lanes past the end recompute the last item so every staged row is finite
+            const long long gi = g0 + (lane < cnt ? lane : cnt - 1);
+            const int b = (int)(gi / A.nitems);
             double s[2 * N_ + 1];
-            stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, t0, lane < cnt ? lane : cnt - 1, s);
+            stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, gi - (long long)b * A.nitems, 0, s);
             double *row = rows + lane * kRowStride;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
@@ -51,8 +56,7 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
             row[slot_e(N_)] = s[N_];
         }
         __syncwarp();
-        const size_t item0 = (size_t)b * A.nitems + t0;
-        mma_tile<N_, MINMODE>(rows, obuf, obuf_s, Bf, G, A.out + item0 * A.L, MINMODE ? A.itemmin + item0 : nullptr,
+        mma_tile<N_, MINMODE>(rows, obuf, obuf_s, Bf, G, A.out + (size_t)g0 * A.L, MINMODE ? A.itemmin + g0 : nullptr,
                                cnt, A.L, A.Lh, A.beta, lane, seq);
         __syncwarp();
     }
@@ -82,7 +86,7 @@ int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t s
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
     if (per_sm < 1) per_sm = 1;
-    const long long nwt = ((A.nitems + 31) / 32) * A.B;
+    const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
     long long grid = (long long)sms * per_sm;
     const long long need = (nwt + kWarps - 1) / kWarps;
     if (grid > need) grid = need;

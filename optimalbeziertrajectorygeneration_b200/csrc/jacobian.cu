@@ -18,7 +18,10 @@
 //   J_SPEED_DIR  item = vehicle v, tf variable (moves control points and the n/tf factor)
 // Output either in the sweep layout [item][L] or scattered into a dense J^T [nvar][ld]
 // (rows of J^T are contiguous, so stores stay coalesced; the host hands SciPy J^T.T).
+#include <stdlib.h>
+
 #include "sq_elev_core.cuh"
+#include "sq_elev_mma.cuh"
 
 namespace {
 using namespace bezcore;
@@ -44,6 +47,126 @@ struct JacArgs {
     double scale;         // alpha * dim / 2
 };
 
+// Stage 1 of the Jacobian kernels for one item: s = B(2a + dx*delta, delta) (unscaled) and
+// the offset of the item's output row.
+template <int N_, int DIM, int JMODE>
+__device__ __forceinline__ void jac_stage1(const JacArgs &A, const FullWeights<N_> &FW,
+                                           const DiffWeights<N_> &DW, long long item,
+                                           double (&s)[2 * N_ + 1], long long &ro) {
+    constexpr int NC = N_ + 1;
+    constexpr int S = (DIM * NC + 1) / 2 * 2;
+    constexpr bool DIRMODE = (JMODE == J_PAIR_DIR || JMODE == J_SPEED_DIR);
+    constexpr int ND = DIRMODE ? DIM : 1;
+    const int dim_ncols = DIM * A.ncols;
+    double a[ND][NC], dl[ND][NC];
+    double dxk;
+    if (JMODE == J_PAIR_VAR) {
+        const long long kk = item / (A.N - 1);
+        const int uu = (int)(item - kk * (A.N - 1));
+        const int v = (int)(kk / dim_ncols);
+        const int rem = (int)(kk - (long long)v * dim_ncols);
+        const int d = rem / A.ncols;
+        const int c = A.offset + (rem - d * A.ncols);
+        const int u = uu + (uu >= v ? 1 : 0);
+        const int vi = v < u ? v : u, vj = v < u ? u : v;
+        const double sg = v < u ? 1.0 : -1.0;
+        const double *pi = A.cpts + (size_t)vi * S + d * NC;
+        const double *pj = A.cpts + (size_t)vj * S + d * NC;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            a[0][k] = __ldg(pi + k) - __ldg(pj + k);
+            dl[0][k] = (k == c) ? sg : 0.0;
+        }
+        dxk = __ldg(A.dx + kk);
+        const long long p = bez_pair_row_offset(vi, A.N) + (vj - vi - 1);
+        ro = A.dense ? kk * A.ld + p * A.L : item * (long long)A.L;
+    } else if (JMODE == J_PAIR_DIR) {
+        int vi, vj;
+        bez_pair_decode(item, A.N, vi, vj);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                a[d][k] = __ldg(A.cpts + (size_t)vi * S + d * NC + k) -
+                          __ldg(A.cpts + (size_t)vj * S + d * NC + k);
+                dl[d][k] = __ldg(A.dir + (size_t)vi * S + d * NC + k) -
+                           __ldg(A.dir + (size_t)vj * S + d * NC + k);
+            }
+        dxk = __ldg(A.dx + A.kdir);
+        ro = A.dense ? (long long)A.kdir * A.ld + item * A.L : item * (long long)A.L;
+    } else if (JMODE == J_SPEED_VAR) {
+        const long long kk = item;
+        const int v = (int)(kk / dim_ncols);
+        const int rem = (int)(kk - (long long)v * dim_ncols);
+        const int d = rem / A.ncols;
+        const int c = A.offset + (rem - d * A.ncols);
+        const double val = (double)N_ / A.tf;
+        const double *pv = A.cpts + (size_t)v * S + d * NC;
+        double pt[NC], dd[NC], de[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) pt[k] = __ldg(pv + k);
+#pragma unroll
+        for (int k = 0; k < N_; ++k) {
+            dd[k] = pt[k] * (-val) + pt[k + 1] * val;
+            de[k] = ((k == c) ? -val : 0.0) + ((k + 1 == c) ? val : 0.0);
+        }
+        dd[N_] = 0.0; de[N_] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            double q = dd[k] * DW.lo[k], r = de[k] * DW.lo[k];
+            if (k > 0) { q = dd[k - 1] * DW.hi[k] + q; r = de[k - 1] * DW.hi[k] + r; }
+            a[0][k] = q;
+            dl[0][k] = r;
+        }
+        dxk = __ldg(A.dx + kk);
+        ro = A.dense ? kk * A.ld + (long long)v * A.L : item * (long long)A.L;
+    } else {   // J_SPEED_DIR: tf moves the control points (dir) and the n/tf factor
+        const int v = (int)item;
+        dxk = __ldg(A.dx + A.kdir);
+        const double val = (double)N_ / A.tf;
+        const double valp = (double)N_ / (A.tf + dxk);
+        const double gam = -(double)N_ / (A.tf * (A.tf + dxk));     // (valp - val) / dx
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            double pt[NC], pd[NC], dd[NC], de[NC];
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                pt[k] = __ldg(A.cpts + (size_t)v * S + d * NC + k);
+                pd[k] = __ldg(A.dir + (size_t)v * S + d * NC + k);
+            }
+#pragma unroll
+            for (int k = 0; k < N_; ++k) {
+                dd[k] = pt[k] * (-val) + pt[k + 1] * val;
+                de[k] = valp * (pd[k + 1] - pd[k]) + gam * (pt[k + 1] - pt[k]);
+            }
+            dd[N_] = 0.0; de[N_] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                double q = dd[k] * DW.lo[k], r = de[k] * DW.lo[k];
+                if (k > 0) { q = dd[k - 1] * DW.hi[k] + q; r = de[k - 1] * DW.hi[k] + r; }
+                a[d][k] = q;
+                dl[d][k] = r;
+            }
+        }
+        ro = A.dense ? (long long)A.kdir * A.ld + (long long)v * A.L : item * (long long)A.L;
+    }
+
+    // s = B(2a + dx*delta, delta)   (Bernstein product, full weight matrix)
+#pragma unroll
+    for (int k = 0; k <= 2 * N_; ++k) s[k] = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        double uvec[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) uvec[i] = fma(dxk, dl[d][i], 2.0 * a[d][i]);
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+                s[i + j] = fma(FW.w[i * NC + j], uvec[i] * dl[d][j], s[i + j]);
+    }
+}
+
 template <int N_, int DIM, int JMODE>
 __global__ void __launch_bounds__(kThreads, 3)
 jac_sq_elev_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeights<N_> DW) {
@@ -51,9 +174,6 @@ jac_sq_elev_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeights<
     constexpr int NT = 2 * N_ + 1;
     constexpr int RS = RowGeom<N_>::RS;
     constexpr int CPL = 2;
-    constexpr int S = (DIM * NC + 1) / 2 * 2;
-    constexpr bool DIRMODE = (JMODE == J_PAIR_DIR || JMODE == J_SPEED_DIR);
-    constexpr int ND = DIRMODE ? DIM : 1;
     extern __shared__ __align__(16) double smem[];
     // layout: [kWarps][32][RS] double2 rows | [NT][LhPad] table | [kWarps][32] row offsets
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,123 +188,16 @@ jac_sq_elev_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeights<
     const long long gwarp = (long long)blockIdx.x * kWarps + warp;
     const long long nwarps = (long long)gridDim.x * kWarps;
     const int ngroups = (A.LhPad / 32 + CPL - 1) / CPL;
-    const int dim_ncols = DIM * A.ncols;
 
     for (long long wt = gwarp; wt < nwt; wt += nwarps) {
         const long long t0 = wt << 5;
         const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
         {
             const long long item = t0 + (lane < cnt ? lane : cnt - 1);
-            double a[ND][NC], dl[ND][NC];
-            double dxk;
-            long long ro;
-            if (JMODE == J_PAIR_VAR) {
-                const long long kk = item / (A.N - 1);
-                const int uu = (int)(item - kk * (A.N - 1));
-                const int v = (int)(kk / dim_ncols);
-                const int rem = (int)(kk - (long long)v * dim_ncols);
-                const int d = rem / A.ncols;
-                const int c = A.offset + (rem - d * A.ncols);
-                const int u = uu + (uu >= v ? 1 : 0);
-                const int vi = v < u ? v : u, vj = v < u ? u : v;
-                const double sg = v < u ? 1.0 : -1.0;
-                const double *pi = A.cpts + (size_t)vi * S + d * NC;
-                const double *pj = A.cpts + (size_t)vj * S + d * NC;
-#pragma unroll
-                for (int k = 0; k < NC; ++k) {
-                    a[0][k] = __ldg(pi + k) - __ldg(pj + k);
-                    dl[0][k] = (k == c) ? sg : 0.0;
-                }
-                dxk = __ldg(A.dx + kk);
-                const long long p = bez_pair_row_offset(vi, A.N) + (vj - vi - 1);
-                ro = A.dense ? kk * A.ld + p * A.L : item * (long long)A.L;
-            } else if (JMODE == J_PAIR_DIR) {
-                int vi, vj;
-                bez_pair_decode(item, A.N, vi, vj);
-#pragma unroll
-                for (int d = 0; d < DIM; ++d)
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        a[d][k] = __ldg(A.cpts + (size_t)vi * S + d * NC + k) -
-                                  __ldg(A.cpts + (size_t)vj * S + d * NC + k);
-                        dl[d][k] = __ldg(A.dir + (size_t)vi * S + d * NC + k) -
-                                   __ldg(A.dir + (size_t)vj * S + d * NC + k);
-                    }
-                dxk = __ldg(A.dx + A.kdir);
-                ro = A.dense ? (long long)A.kdir * A.ld + item * A.L : item * (long long)A.L;
-            } else if (JMODE == J_SPEED_VAR) {
-                const long long kk = item;
-                const int v = (int)(kk / dim_ncols);
-                const int rem = (int)(kk - (long long)v * dim_ncols);
-                const int d = rem / A.ncols;
-                const int c = A.offset + (rem - d * A.ncols);
-                const double val = (double)N_ / A.tf;
-                const double *pv = A.cpts + (size_t)v * S + d * NC;
-                double pt[NC], dd[NC], de[NC];
-#pragma unroll
-                for (int k = 0; k < NC; ++k) pt[k] = __ldg(pv + k);
-#pragma unroll
-                for (int k = 0; k < N_; ++k) {
-                    dd[k] = pt[k] * (-val) + pt[k + 1] * val;
-                    de[k] = ((k == c) ? -val : 0.0) + ((k + 1 == c) ? val : 0.0);
-                }
-                dd[N_] = 0.0; de[N_] = 0.0;
-#pragma unroll
-                for (int k = 0; k < NC; ++k) {
-                    double q = dd[k] * DW.lo[k], r = de[k] * DW.lo[k];
-                    if (k > 0) { q = dd[k - 1] * DW.hi[k] + q; r = de[k - 1] * DW.hi[k] + r; }
-                    a[0][k] = q;
-                    dl[0][k] = r;
-                }
-                dxk = __ldg(A.dx + kk);
-                ro = A.dense ? kk * A.ld + (long long)v * A.L : item * (long long)A.L;
-            } else {   // J_SPEED_DIR: tf moves the control points (dir) and the n/tf factor
-                const int v = (int)item;
-                dxk = __ldg(A.dx + A.kdir);
-                const double val = (double)N_ / A.tf;
-                const double valp = (double)N_ / (A.tf + dxk);
-                const double gam = -(double)N_ / (A.tf * (A.tf + dxk));     // (valp - val) / dx
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) {
-                    double pt[NC], pd[NC], dd[NC], de[NC];
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        pt[k] = __ldg(A.cpts + (size_t)v * S + d * NC + k);
-                        pd[k] = __ldg(A.dir + (size_t)v * S + d * NC + k);
-                    }
-#pragma unroll
-                    for (int k = 0; k < N_; ++k) {
-                        dd[k] = pt[k] * (-val) + pt[k + 1] * val;
-                        de[k] = valp * (pd[k + 1] - pd[k]) + gam * (pt[k + 1] - pt[k]);
-                    }
-                    dd[N_] = 0.0; de[N_] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        double q = dd[k] * DW.lo[k], r = de[k] * DW.lo[k];
-                        if (k > 0) { q = dd[k - 1] * DW.hi[k] + q; r = de[k - 1] * DW.hi[k] + r; }
-                        a[d][k] = q;
-                        dl[d][k] = r;
-                    }
-                }
-                ro = A.dense ? (long long)A.kdir * A.ld + (long long)v * A.L : item * (long long)A.L;
-            }
-            rowoff[lane] = ro;
-
-            // s = B(2a + dx*delta, delta)   (Bernstein product, full weight matrix)
             double s[2 * N_ + 1];
-#pragma unroll
-            for (int k = 0; k <= 2 * N_; ++k) s[k] = 0.0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                double uvec[NC];
-#pragma unroll
-                for (int i = 0; i < NC; ++i) uvec[i] = fma(dxk, dl[d][i], 2.0 * a[d][i]);
-#pragma unroll
-                for (int i = 0; i < NC; ++i)
-#pragma unroll
-                    for (int j = 0; j < NC; ++j)
-                        s[i + j] = fma(FW.w[i * NC + j], uvec[i] * dl[d][j], s[i + j]);
-            }
+            long long ro;
+            jac_stage1<N_, DIM, JMODE>(A, FW, DW, item, s, ro);
+            rowoff[lane] = ro;
             double2 *row = rows + (size_t)lane * RS;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
@@ -202,6 +215,79 @@ jac_sq_elev_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeights<
         }
         __syncwarp();
     }
+}
+
+// Sweep-layout variant on the fp64 tensor path (sq_elev_mma.cuh): the rows of consecutive
+// items are contiguous, so the DMMA stage 2 + TMA bulk-store epilogue of the constraint
+// kernels applies unchanged.  Used for the per-variable modes (one dimension live in stage 1).
+template <int N_, int DIM, int JMODE>
+__global__ void __launch_bounds__(kThreads, 2)
+jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeights<N_> DW) {
+    using namespace bezmma;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t per_warp = (size_t)kRowsDoubles + 16 * (size_t)A.L + 32;
+    double *rows = smem + warp * per_warp;
+    double *obuf = rows + kRowsDoubles;
+    for (int i = lane; i < kRowsDoubles; i += 32) rows[i] = 0.0;     // padding slots must be 0
+    const unsigned obuf_s = (unsigned)__cvta_generic_to_shared(obuf);
+    const LaneGeom G = lane_geom(lane, A.Lh);
+    BFrags<N_> Bf;
+    load_bfrags<N_>(Bf, A.PQ, A.Lh, A.LhPad, lane);
+    __syncwarp();
+    const long long nwt = (A.nitems + 31) >> 5;
+    const long long gwarp = (long long)blockIdx.x * kWarps + warp;
+    const long long nwarps = (long long)gridDim.x * kWarps;
+    unsigned seq = 0;
+    for (long long wt = gwarp; wt < nwt; wt += nwarps) {
+        const long long t0 = wt << 5;
+        const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
+        {
+            double s[2 * N_ + 1];
+            long long ro;
+            jac_stage1<N_, DIM, JMODE>(A, FW, DW, t0 + (lane < cnt ? lane : cnt - 1), s, ro);
+            double *row = rows + lane * kRowStride;
+#pragma unroll
+            for (int j = 0; j < N_; ++j) {
+                const double lo = s[j] * A.scale, hi = s[2 * N_ - j] * A.scale;
+                row[slot_e(j)] = lo + hi;
+                row[slot_o(j)] = lo - hi;
+            }
+            row[slot_e(N_)] = s[N_] * A.scale;
+        }
+        __syncwarp();
+        mma_tile<N_, 0>(rows, obuf, obuf_s, Bf, G, A.out + (size_t)t0 * A.L, nullptr, cnt, A.L, A.Lh, 0.0, lane, seq);
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+template <int N_, int DIM, int JMODE>
+int launch_jac_mma(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
+    FullWeights<N_> FW;
+    DiffWeights<N_> DW;
+    for (int i = 0; i < (N_ + 1) * (N_ + 1); ++i) FW.w[i] = plan->h_W[i];
+    for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
+    const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L + 32) * sizeof(double);
+    auto kern = jac_sq_elev_mma_kernel<N_, DIM, JMODE>;
+    static size_t attr_set = 0;
+    if (shmem > attr_set) {
+        BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        attr_set = shmem;
+    }
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
+    if (per_sm < 1) per_sm = 1;
+    const long long nwt = (A.nitems + 31) / 32;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (nwt + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) return BEZ_OK;
+    kern<<<(unsigned)grid, kThreads, shmem, st>>>(A, FW, DW);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
 }
 
 template <int N_, int DIM, int JMODE>
@@ -240,6 +326,16 @@ int launch_jac(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
 
 template <int N_, int JMODE>
 int jdispatch_dim(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
+    if constexpr (JMODE == J_PAIR_VAR || JMODE == J_SPEED_VAR) {
+        const char *e = getenv("BEZGPU_FORCE_DFMA");
+        if (!A.dense && A.Lh > 32 && A.Lh <= 64 && !(e && e[0] == '1')) {
+            switch (plan->dim) {
+                case 1: return launch_jac_mma<N_, 1, JMODE>(plan, A, st);
+                case 2: return launch_jac_mma<N_, 2, JMODE>(plan, A, st);
+                case 3: return launch_jac_mma<N_, 3, JMODE>(plan, A, st);
+            }
+        }
+    }
     switch (plan->dim) {
         case 1: return launch_jac<N_, 1, JMODE>(plan, A, st);
         case 2: return launch_jac<N_, 2, JMODE>(plan, A, st);
@@ -252,8 +348,12 @@ template <int JMODE>
 int jdispatch(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
     switch (plan->n) {
 #define CASE(n_) case n_: return jdispatch_dim<n_, JMODE>(plan, A, st);
+#ifdef BEZ_ONLY_N   /* development builds: one degree only (fast compile) */
+        CASE(BEZ_ONLY_N)
+#else
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
         CASE(9) CASE(10) CASE(11) CASE(12)
+#endif
 #undef CASE
     }
     bez_set_error("degree %d has no Jacobian kernel instantiation (1..12 supported)", plan->n);
@@ -282,6 +382,30 @@ __global__ void fd_quotient_kernel(const double *__restrict__ F, const double *_
 }
 
 }  // namespace
+
+static __global__ void fd_quotient_batched_kernel(const double *__restrict__ F, const double *__restrict__ dx,
+                                           long long count, int nvar, long long m, double *__restrict__ JT) {
+    const long long per = (long long)nvar * m, total = count * per;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / per, rem = idx - p * per;
+        const long long k = rem / m, r = rem - k * m;
+        const double *Fp = F + p * (nvar + 1) * m;
+        JT[idx] = __ddiv_rn(__dsub_rn(Fp[(k + 1) * m + r], Fp[r]), __ldg(dx + p * nvar + k));
+    }
+}
+
+extern "C" int bez_fd_quotient_batched(const double *d_F, const double *d_dx, int64_t count, int nvar,
+                                       int64_t m, double *d_JT, void *stream) {
+    BEZ_REQUIRE(d_F && d_dx && d_JT, "NULL argument");
+    BEZ_REQUIRE(count >= 0 && nvar >= 0 && m >= 0, "negative size");
+    if (count == 0 || nvar == 0 || m == 0) return BEZ_OK;
+    long long blocks = ((long long)count * nvar * m + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    fd_quotient_batched_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_F, d_dx, count, nvar, m, d_JT);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
 
 extern "C" int bez_fd_quotient(const double *d_F, const double *d_dx, int nvar, int64_t m,
                                double *d_JT, void *stream) {

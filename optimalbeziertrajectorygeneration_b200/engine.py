@@ -189,18 +189,25 @@ class ConstraintEngine:
         return host.copy() if copy else host
 
     # -- A0 -----------------------------------------------------------------
-    def assemble(self, d_x, elev=0):
+    def assemble(self, d_x, elev=0, obst_sets=None, evals_per_set=0):
         """reshapeVector (+ obstacle rows) for every row of d_x [B, nvar].
-        Returns (cpts [B, N, S], tf [B]) with S = dim*(n+1) rounded up to even."""
+        Returns (cpts [B, N, S], tf [B]) with S = dim*(n+1) rounded up to even.
+        ``obst_sets`` [nsets, nObs, dim] (device) with ``evals_per_set`` > 0: row b takes the
+        obstacles of set b // evals_per_set (batches of independent problems, batch.py)."""
         B = int(d_x.shape[0])
         plan = self.plan(elev)
         cpts = torch.empty((B, self.N, self.row_stride), dtype=F64, device=self.device)
         tf = torch.empty((B,), dtype=F64, device=self.device)
-        _capi.call("bez_assemble_cpts", plan.handle, _ptr(d_x), B, self.nvar, self.numVeh, self.nObs,
+        if obst_sets is not None:
+            if tuple(obst_sets.shape[1:]) != (self.nObs, self.dim) or evals_per_set <= 0 or \
+                    int(obst_sets.shape[0]) * evals_per_set < B:
+                raise ValueError("obstacle sets do not cover the %d evaluation points" % B)
+        _capi.call("bez_assemble_cpts_sets", plan.handle, _ptr(d_x), B, self.nvar, self.numVeh, self.nObs,
                    int(self.fixed_ends), int(self.dubins), int(self.timeopt), self.tf_fixed,
                    _ptr(self.d_init), _ptr(self.d_final), _ptr(self.d_ispeed), _ptr(self.d_fspeed),
                    _ptr(self.d_icos), _ptr(self.d_isin), _ptr(self.d_fcos), _ptr(self.d_fsin),
-                   _ptr(self.d_obst), _ptr(cpts), _ptr(tf), _stream())
+                   _ptr(self.d_obst if obst_sets is None else obst_sets),
+                   int(evals_per_set) if obst_sets is not None else 0, _ptr(cpts), _ptr(tf), _stream())
         return cpts, tf
 
     # -- A1-A4 --------------------------------------------------------------
