@@ -335,11 +335,13 @@ def run_ours(opts):
     if not opts.no_sweep:
         torch.cuda.empty_cache()
         J = eng.jac_separation(x, E, dense=False)
+        for _ in range(2):
+            eng.jac_separation(x, E, dense=False, out=J)
         torch.cuda.synchronize()
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a_.record()
         for _ in range(3):
-            J = eng.jac_separation(x, E, dense=False)
+            eng.jac_separation(x, E, dense=False, out=J)
         b_.record()
         torch.cuda.synchronize()
         sms = a_.elapsed_time(b_) / 3

@@ -285,9 +285,10 @@ class ConstraintEngine:
             self._dir = D
         return self._dir
 
-    def jac_separation(self, x, elev, dense=True):
+    def jac_separation(self, x, elev, dense=True, out=None):
         """FD Jacobian of the separation block at x (host vector).
-        dense: returns J^T as a device tensor [nvar, P*L]; else the sweep layout."""
+        dense: returns J^T as a device tensor [nvar, P*L]; else the sweep layout.
+        ``out``: preallocated destination of the right shape (sweep layout only)."""
         plan = self.plan(elev)
         x = np.asarray(x, dtype=np.float64)
         _, dx = self.fd_steps(x)
@@ -303,7 +304,11 @@ class ConstraintEngine:
                 out[self.nvar - 1].zero_()          # tf does not move any control point
             ld = P * L
         else:
-            out = torch.empty((nvarN * (self.N - 1) + (P if kdir >= 0 else 0), L), dtype=F64, device=self.device)
+            shape = (nvarN * (self.N - 1) + (P if kdir >= 0 else 0), L)
+            if out is None:
+                out = torch.empty(shape, dtype=F64, device=self.device)
+            elif tuple(out.shape) != shape or out.dtype != F64 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous float64 tensor of shape %r" % (shape,))
             ld = 0
         _capi.call("bez_jac_sepsq_elev", plan.handle, _ptr(cpts), self.N, self.numVeh, self.ncols,
                    self.offset, _ptr(d_dx), _ptr(dirs), kdir, int(dense), _ptr(out), ld, _stream())
