@@ -64,3 +64,59 @@ def gather_pair_minima(local, mode="batch", total=None):
         b, e = block_range(total, world, r)
         parts.append(buf[r, :, :e - b])
     return torch.cat(parts, dim=1)
+
+
+class PairMinimaGatherer:
+    """Overlapped form of gather_pair_minima(mode='batch') for a stream of steps: the
+    all-gather of step k runs on its own CUDA stream while the kernels of step k+1 run
+    on the caller's stream (two local/gathered buffer pairs, events, no host sync).
+
+        g = PairMinimaGatherer(B, P, device)
+        for step in ...:
+            local = g.local_buffer()          # [B, P] the kernels of this step write into
+            ... launch kernels writing `local` on the current stream ...
+            gathered = g.gather()             # [world*B, P]; valid after g.wait() / g.finish()
+        g.finish()
+    """
+
+    def __init__(self, B, P, device, dtype=torch.float64):
+        self.rank, self.world = world_info()
+        self.local = [torch.empty((B, P), dtype=dtype, device=device) for _ in range(2)]
+        self.full = [torch.empty((self.world * B, P), dtype=dtype, device=device) for _ in range(2)] \
+            if self.world > 1 else self.local
+        # CPU tensors (gloo, host-logic tests): same buffer rotation, synchronous collective
+        self.cuda = torch.device(device).type == "cuda"
+        self.stream = torch.cuda.Stream(device=device) if (self.world > 1 and self.cuda) else None
+        self.done = [None, None]
+        self.k = 0
+
+    def local_buffer(self):
+        """Buffer for the next step; waits (on the current stream) until the gather that last
+        read it has finished."""
+        i = self.k & 1
+        if self.done[i] is not None and self.cuda:
+            torch.cuda.current_stream().wait_event(self.done[i])
+        return self.local[i]
+
+    def gather(self):
+        i = self.k & 1
+        self.k += 1
+        if self.world == 1:
+            return self.local[i]
+        if not self.cuda:
+            dist.all_gather_into_tensor(self.full[i], self.local[i])
+            return self.full[i]
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            dist.all_gather_into_tensor(self.full[i], self.local[i])
+            self.done[i] = torch.cuda.Event()
+            self.done[i].record(self.stream)
+        return self.full[i]
+
+    def finish(self):
+        """Makes the current stream wait for every outstanding gather."""
+        for ev in self.done:
+            if ev is not None and self.cuda:
+                torch.cuda.current_stream().wait_event(ev)

@@ -45,7 +45,15 @@ def _worker(rank, world, port, q):
         b, e = sharding.block_range(P, world, rank)
         got2 = sharding.gather_pair_minima(one[:, b:e].clone(), mode="pairs", total=P)
         ok2 = torch.equal(got2, one)
-        q.put((rank, bool(ok1), bool(ok2)))
+        # the overlapped gatherer (synchronous on CPU): buffer rotation over several steps
+        g = sharding.PairMinimaGatherer(B, P, "cpu")
+        ok3 = True
+        for step in range(5):
+            loc = g.local_buffer()
+            loc.copy_(full[rank * B:(rank + 1) * B] + step)
+            ok3 = ok3 and torch.equal(g.gather(), full + step)
+        g.finish()
+        q.put((rank, bool(ok1), bool(ok2 and ok3)))
     finally:
         dist.destroy_process_group()
 
