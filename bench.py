@@ -180,11 +180,11 @@ def run_reference(opts):
     print(json.dumps(line))
 
 
-def workload_config(B):
+def workload_config(B, gather_mode="n/a"):
     return {"workload": "C4 synthetic swarm: N=1024 vehicles, dim 3, degree 10, DEG_ELEV 100, "
                         "all 523776 pairs x 121 separation values + 1024 x 121 max-speed values per eval",
             "evals_per_step_per_gpu": B, "sharding": "FD-perturbation batch split across ranks; "
-            "all-gather of the [B,P] per-pair minimum", "l2_policy": "outputs (508 MB/eval) >> 126 MB L2, "
+            "all-gather of the [B,P] per-pair minimum", "gather": gather_mode, "l2_policy": "outputs (508 MB/eval) >> 126 MB L2, "
             "streaming stores; inputs 270 KB"}
 
 
@@ -219,16 +219,32 @@ def run_ours(opts):
     pairmin = torch.empty((B, P), dtype=torch.float64, device=eng.device)
     max_speed2 = float(args["maxSpeed"]) ** 2
 
-    gatherer = sharding.PairMinimaGatherer(B, P, eng.device)
+    # The one collective of the path: every rank ends up with the whole [world*B, P] per-pair
+    # minimum (active-pair) matrix.  Preferred: fused into the pair kernel (NVLink peer stores
+    # into symmetric memory, sharding.PeerMinima); fallback: NCCL all-gather on its own stream.
+    gatherer, peer, gather_mode = None, None, "none (1 GPU)"
+    if world > 1 and not opts.nccl_gather:
+        try:
+            peer = sharding.PeerMinima(B, P, eng.device)
+            gather_mode = "fused: in-kernel NVLink peer stores into symmetric memory + signal-pad barrier"
+        except Exception as e:                      # symmetric memory not available on this box
+            if rank == 0:
+                print("PeerMinima unavailable (%r); falling back to NCCL all-gather" % (e,), file=sys.stderr)
+    if peer is None:
+        gatherer = sharding.PairMinimaGatherer(B, P, eng.device)
+        if world > 1:
+            gather_mode = "NCCL all_gather_into_tensor on a side stream"
 
     def step():
         cpts, tf = eng.assemble(d_x, E)
+        if peer is not None:
+            pm, peers = peer.targets()
+            eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pm, peer_ptrs=peers)
+            eng.speed(cpts, tf, E, -1.0, max_speed2, out=out_spd)
+            return peer.complete()
         pm = gatherer.local_buffer()
         eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pm)
         eng.speed(cpts, tf, E, -1.0, max_speed2, out=out_spd)
-        # the one collective of the path: every rank ends up with the whole [world*B, P]
-        # per-pair minimum (active-pair) matrix; it runs on its own stream and overlaps the
-        # kernels of the next step (the timed region ends after the last gather has finished)
         return gatherer.gather()
     launches_per_step = 3       # assemble, fused pair kernel (values + per-pair min), speed kernel
 
@@ -239,7 +255,8 @@ def run_ours(opts):
 
     for _ in range(max(3, opts.warmup)):
         step()
-    gatherer.finish()
+    if gatherer is not None:
+        gatherer.finish()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -247,14 +264,23 @@ def run_ours(opts):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(opts.steps):
-        step()
-    gatherer.finish()
+        gathered = step()
+    if gatherer is not None:
+        gatherer.finish()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # self-check of the collective (outside the timed region): the gathered matrix of the
+        # last step must equal a plain NCCL all-gather of the per-rank minima, bit for bit
+        mine = gathered[rank * B:(rank + 1) * B].clone()
+        ref = torch.empty((world * B, P), dtype=torch.float64, device=eng.device)
+        dist.all_gather_into_tensor(ref, mine)
+        torch.cuda.synchronize()
+        assert torch.equal(ref, gathered), "gathered per-pair minima differ from the NCCL all-gather"
+        assert torch.equal(mine, out_sep.min(dim=2).values), "per-pair minima differ from the row minima"
     ms = float(t.item())
 
     # dominant kernel alone (pair kernel), CUDA events on its stream
@@ -380,7 +406,7 @@ def run_ours(opts):
                 "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
                 "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(B),
+                "config": workload_config(B, gather_mode),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "kernel": "sq_elev_mma_kernel<10,3,PAIR,min> (DMMA.8x8x4 stage 2, TMA bulk-store epilogue)",
@@ -508,6 +534,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="evals (x vectors) per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="multi-GPU: use the NCCL all-gather instead of the fused in-kernel peer stores")
     ap.add_argument("--no-sweep", action="store_true", help="skip the closed-form Jacobian sweep leg")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4 = the headline swarm (default); c5 = batch of independent Dubins problems")

@@ -111,6 +111,18 @@ int bez_assemble_cpts_sets(const bez_plan *plan, const double *d_x, int B, int n
 int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, int B, int N,
                         int64_t pair_begin, int64_t npairs, double maxSep2,
                         double *d_out, double *d_pairmin, void *stream);
+/* The same kernel fused with the one collective of the path (all-gather of
+ * the per-pair minima): every minimum is stored to d_pairmin AND, from inside the kernel,
+ * to npeers <= BEZ_MAX_PEERS peer-GPU buffers over NVLink (h_peer_min: host array of
+ * device pointers into the peers' gathered [world*B][npairs] matrices, each already offset
+ * to this rank's block; peer access / symmetric memory is set up by the caller).  The
+ * data is complete on a peer once this kernel has finished on every rank (stream-ordered
+ * barrier by the caller).  BEZ_EUNSUPPORTED for shapes outside the tensor-path kernels. */
+#define BEZ_MAX_PEERS 7
+int bez_pair_sepsq_elev_p2p(const bez_plan *plan, const double *d_cpts, int B, int N,
+                            int64_t pair_begin, int64_t npairs, double maxSep2,
+                            double *d_out, double *d_pairmin,
+                            const uint64_t *h_peer_min, int npeers, void *stream);
 
 /* ---- A5: _maxSpeedConstraints / _minSpeedConstraints (optimization.py:349-422)
  * = Bezier.diff (bezier.py:497-519, same degree) -> normSquare ->

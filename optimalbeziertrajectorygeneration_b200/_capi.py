@@ -43,6 +43,7 @@ SIGNATURES = {
     "bez_assemble_cpts_sets": (I, [c_plan_p, P, I, I, I, I, I, I, I, D,
                                    P, P, P, P, P, P, P, P, P, I, P, P, P]),
     "bez_pair_sepsq_elev": (I, [c_plan_p, P, I, I, L64, L64, D, P, P, P]),
+    "bez_pair_sepsq_elev_p2p": (I, [c_plan_p, P, I, I, L64, L64, D, P, P, P, I, P]),
     "bez_speed_sq_elev": (I, [c_plan_p, P, P, I, I, I, I, D, D, P, P]),
     "bez_angrate_tables_create": (I, [I, I, I, P, P, P, P, ctypes.POINTER(c_plan_p)]),
     "bez_angrate_tables_destroy": (I, [c_plan_p]),

@@ -259,9 +259,36 @@ extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, i
     A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = d_pairmin;
     A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
-    A.alpha = 1.0; A.beta = -maxSep2;
+    A.alpha = 1.0; A.beta = -maxSep2; A.npeers = 0;
     if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, PAIR, (cudaStream_t)stream);
     return dispatch_degree<PAIR>(plan, A, (cudaStream_t)stream);
+}
+
+extern "C" int bez_pair_sepsq_elev_p2p(const bez_plan *plan, const double *d_cpts, int B, int N,
+                                       int64_t pair_begin, int64_t npairs, double maxSep2,
+                                       double *d_out, double *d_pairmin,
+                                       const uint64_t *h_peer_min, int npeers, void *stream) {
+    BEZ_REQUIRE(plan && d_cpts && d_out && d_pairmin, "NULL argument");
+    BEZ_REQUIRE(B >= 0 && N >= 0, "negative size");
+    BEZ_REQUIRE(npeers >= 0 && npeers <= BEZ_MAX_PEERS && (npeers == 0 || h_peer_min), "bad peer list");
+    const long long P = (long long)N * (N - 1) / 2;
+    BEZ_REQUIRE(pair_begin >= 0 && npairs >= 0 && pair_begin + npairs <= (P > 0 ? P : 0),
+                "pair range outside the N(N-1)/2 list");
+    if (!bez_sq_elev_mma_supported(plan)) {
+        bez_set_error("bez_pair_sepsq_elev_p2p: degree %d / elevation %d is outside the tensor-path kernels",
+                      plan->n, plan->elev);
+        return BEZ_EUNSUPPORTED;
+    }
+    if (B == 0 || npairs == 0) return BEZ_OK;
+    BEZ_CUDA(cudaSetDevice(plan->device));
+    SqElevArgs A;
+    A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = d_pairmin;
+    A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
+    A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
+    A.alpha = 1.0; A.beta = -maxSep2; A.npeers = npeers;
+    for (int q = 0; q < BEZ_MAX_PEERS; ++q)
+        A.peer_min[q] = q < npeers ? reinterpret_cast<double *>((uintptr_t)h_peer_min[q]) : nullptr;
+    return bez_sq_elev_mma(plan, A, PAIR, (cudaStream_t)stream);
 }
 
 extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, const double *d_tf,
@@ -276,7 +303,7 @@ extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, con
     A.cpts = d_cpts; A.tf = d_tf; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = nullptr;
     A.item_begin = veh_begin; A.nitems = nveh; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
-    A.alpha = alpha; A.beta = beta;
+    A.alpha = alpha; A.beta = beta; A.npeers = 0;
     if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, SPEED, (cudaStream_t)stream);
     return dispatch_degree<SPEED>(plan, A, (cudaStream_t)stream);
 }

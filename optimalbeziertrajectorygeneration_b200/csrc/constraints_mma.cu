@@ -57,7 +57,7 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
         }
         __syncwarp();
         mma_tile<N_, MINMODE>(rows, obuf, obuf_s, Bf, G, A.out + (size_t)g0 * A.L, MINMODE ? A.itemmin + g0 : nullptr,
-                               cnt, A.L, A.Lh, A.beta, lane, seq);
+                               cnt, A.L, A.Lh, A.beta, lane, seq, A.peer_min, MINMODE ? A.npeers : 0, g0);
         __syncwarp();
     }
     if (lane == 0) bulk_wait_all();      // staging buffers must outlive the last bulk reads

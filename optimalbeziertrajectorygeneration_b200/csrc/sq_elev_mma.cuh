@@ -126,7 +126,8 @@ template <int N_, int MINMODE>
 __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
                                          const BFrags<N_> &B, const LaneGeom &G,
                                          double *__restrict__ outg, double *__restrict__ ming, int cnt,
-                                         int L, int Lh, double beta, int lane, unsigned &seq) {
+                                         int L, int Lh, double beta, int lane, unsigned &seq,
+                                         double *const *peer_min = nullptr, int npeers = 0, long long peer_off = 0) {
     constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO;
     const int g = G.g, t = G.t;
     const int M = L - 1;
@@ -227,7 +228,12 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
             mnv[mi] = dmin(mnv[mi], __shfl_xor_sync(0xffffffffu, mnv[mi], 2));
         }
         const double v = t == 0 ? mnv[0] : t == 1 ? mnv[1] : t == 2 ? mnv[2] : mnv[3];
-        if (8 * t + g < cnt) ming[8 * t + g] = v;
+        if (8 * t + g < cnt) {
+            ming[8 * t + g] = v;
+#pragma unroll
+            for (int q = 0; q < BEZ_MAX_PEERS; ++q)         // fused all-gather: NVLink peer stores
+                if (q < npeers) peer_min[q][peer_off + 8 * t + g] = v;
+        }
     }
 }
 

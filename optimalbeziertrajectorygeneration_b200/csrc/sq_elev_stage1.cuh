@@ -17,6 +17,11 @@ struct SqElevArgs {
     long long nitems;       // pairs / vehicles per evaluation point
     int B, N, L, Lh, LhPad;
     double alpha, beta;     // out = alpha * value + beta   (alpha = +-1)
+    // Fused all-gather of the per-item minima over NVLink peer memory (tensor path only):
+    // every minimum is also stored to npeers other GPUs' gathered matrices (pointers already
+    // offset to this rank's block), so no collective follows the kernel.
+    double *peer_min[BEZ_MAX_PEERS];
+    int npeers;
 };
 
 // Stage 1 for one item (lane = item): the 2n+1 Bernstein coefficients (before the

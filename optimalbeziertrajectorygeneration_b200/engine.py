@@ -212,9 +212,11 @@ class ConstraintEngine:
 
     # -- A1-A4 --------------------------------------------------------------
     def separation(self, cpts, elev, max_sep, pair_begin=0, npairs=None, out=None, pairmin=None,
-                   n_curves=None):
+                   n_curves=None, peer_ptrs=None):
         """Fused sub -> normSquare -> elev -> -maxSep^2 over a range of the
-        lexicographic pair list.  Returns out [B, npairs, L] (device)."""
+        lexicographic pair list.  Returns out [B, npairs, L] (device).
+        ``peer_ptrs``: device addresses in other GPUs' gathered per-pair-minimum matrices
+        (sharding.PeerMinima); the kernel then also stores every minimum there over NVLink."""
         plan = self.plan(elev)
         B = int(cpts.shape[0])
         N = int(cpts.shape[1]) if n_curves is None else int(n_curves)
@@ -222,6 +224,14 @@ class ConstraintEngine:
             npairs = num_pairs(N) - pair_begin
         if out is None:
             out = torch.empty((B, npairs, plan.L), dtype=F64, device=self.device)
+        if peer_ptrs:
+            if pairmin is None:
+                raise ValueError("peer_ptrs needs the local pairmin destination")
+            arr = (ctypes.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+            _capi.call("bez_pair_sepsq_elev_p2p", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
+                       float(max_sep) ** 2, _ptr(out), _ptr(pairmin), ctypes.addressof(arr), len(peer_ptrs),
+                       _stream())
+            return out
         _capi.call("bez_pair_sepsq_elev", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
                    float(max_sep) ** 2, _ptr(out), _ptr(pairmin), _stream())
         return out

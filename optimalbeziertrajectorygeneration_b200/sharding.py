@@ -120,3 +120,48 @@ class PairMinimaGatherer:
         for ev in self.done:
             if ev is not None and self.cuda:
                 torch.cuda.current_stream().wait_event(ev)
+
+
+class PeerMinima:
+    """The all-gather of the per-pair minima fused into the pair kernel: the gathered
+    [world*B, P] matrix of every rank lives in symmetric memory (torch.distributed
+    ._symmetric_memory: peer-mapped device buffers over NVLink / NVSwitch), and each rank's
+    kernel stores its minima into its block of *every* rank's matrix while it computes
+    (8 bytes per pair per peer next to 976 bytes per pair of HBM traffic), so no collective
+    kernel follows.  Completion = every rank has finished its kernel: a stream-ordered
+    symmetric-memory barrier.  Two matrices are rotated so that step k+1 may start while the
+    consumer still reads step k.
+
+        pm = PeerMinima(B, P, device)                  # collective (rendezvous)
+        local, peers = pm.targets()                    # this step's destinations
+        eng.separation(cpts, E, maxSep, out=..., pairmin=local, peer_ptrs=peers)
+        gathered = pm.complete()                       # [world*B, P], valid in stream order
+    """
+
+    def __init__(self, B, P, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = world_info()
+        if self.world > 8:
+            raise ValueError("PeerMinima supports one NVLink domain of up to 8 GPUs")
+        self.B, self.P = int(B), int(P)
+        group = dist.group.WORLD if group is None else group
+        self.buf = symm_mem.empty((2, self.world * self.B, self.P), dtype=torch.float64, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.k = 0
+
+    def targets(self):
+        """(local [B, P] view, list of peer device addresses) for the current step."""
+        i = self.k & 1
+        block = (i * self.world * self.B + self.rank * self.B) * self.P * 8
+        local = self.buf[i, self.rank * self.B:(self.rank + 1) * self.B]
+        peers = [self.ptrs[r] + block for r in range(self.world) if r != self.rank]
+        return local, peers
+
+    def complete(self):
+        """Stream-ordered: returns the gathered matrix of the current step once every rank's
+        kernel has finished (barrier on the symmetric-memory signal pads), then rotates."""
+        i = self.k & 1
+        self.hdl.barrier(channel=i)
+        self.k += 1
+        return self.buf[i]

@@ -1,0 +1,67 @@
+"""Two-GPU check of the fused all-gather (in-kernel NVLink peer stores into symmetric
+memory) against a plain NCCL all-gather.  Skipped on boxes with fewer than two GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle.make_golden import synthetic_swarm_args
+    from optimalbeziertrajectorygeneration_b200 import optimization as gopt
+    from optimalbeziertrajectorygeneration_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        args, x = synthetic_swarm_args(70)
+        b = gopt.BezOptimization(**args)
+        eng = b._engine(True)
+        B, E = 3, 100
+        X = x[None, :] + np.random.default_rng(rank).normal(size=(B, x.size)) * 0.05
+        cpts, _ = eng.assemble(eng.upload(X), E)
+        P = 70 * 69 // 2
+        pm = sharding.PeerMinima(B, P, eng.device)
+        ok = True
+        for step in range(3):
+            local, peers = pm.targets()
+            sep = eng.separation(cpts, E, 0.9, pairmin=local, peer_ptrs=peers)
+            gathered = pm.complete()
+            ref = torch.empty((world * B, P), dtype=torch.float64, device=eng.device)
+            dist.all_gather_into_tensor(ref, sep.min(dim=2).values.contiguous())
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(ref, gathered)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_fused_allgather_matches_nccl():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res)
