@@ -145,6 +145,221 @@ __global__ void __launch_bounds__(kAThreads) angrate_kernel(const AngArgs A) {
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Second-generation kernel: one WARP per (evaluation point, vehicle), register-tiled and
+// load-balanced Bernstein products.
+//
+// A product c_k = sum_i a_i b_{k-i} of two length-La sequences has 2 La - 1 outputs whose term
+// counts form a triangle.  Outputs are cut into tiles of R consecutive k; lane j owns tile j
+// ("phase A", terms i = 0 .. R j + R - 1) and tile j + H ("phase B", terms i = R (j+H) - La + 1
+// .. La - 1): the two term counts add up to the same S = 2 La + R - 1 - R H for every lane, so
+// all lanes run the same S steps in lockstep and only the step at which a lane flips from its
+// first to its second tile differs (lane j flips at step R (j+1), i.e. exactly one lane flips
+// at each R-step segment boundary).  In one step a lane loads one a_i per factor, slides an
+// R-wide register window over b (one new element per step) and issues R DFMAs per product:
+// R = 8 for the two degree-2m squares (4 LDS : 16 DFMA), R = 4 for the four degree-m products
+// (6 LDS : 16 DFMA).  The first kernel spent one LDS per 2 (squares) or 0.7 (products) DFMAs
+// and ran at 0.17 of the fp64 pipe on C5.
+// Shared-memory rows use the index maps i -> i + i/8 (NUM, DEN) and i -> i + i/4 (derivative
+// rows) so that the window loads of 32 lanes, R doubles apart, are bank-conflict free; guard
+// zones of zeros around every row stand in for the ragged ends of the triangle.
+// Requires ceil((4m+1)/8) <= 64, i.e. m <= 127; larger m uses angrate_kernel.
+constexpr int kWarpsW = 4;
+constexpr int kGuard = 16;                      // logical guard on both sides of every padded row
+
+__device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
+__device__ __forceinline__ int pad4(int i) { return i + (i >> 2); }
+
+struct WarpPlan {            // host-computed geometry of the two tiled phases
+    int H1, nseg1, H2, nseg2;
+    int lenP4, lenP8;        // doubles per pad4 / pad8 row (with guards)
+    int per_warp;            // doubles of shared memory per warp
+};
+
+__global__ void __launch_bounds__(32 * kWarpsW) angrate_warp_kernel(const AngArgs A, const WarpPlan W) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * kWarpsW + warp;
+    if (item >= (long long)A.B * A.nveh) return;                 // whole warp; no block-wide barriers below
+    const int m = A.m, n = A.n, m1 = m + 1, L2 = 2 * m + 1, L4 = 4 * m + 1;
+    double *base = sm + (size_t)warp * W.per_warp;
+    double *px = base, *py = px + m1, *tmpx = py + m1, *tmpy = tmpx + m1;
+    double *XD = tmpy + m1 + pad4(kGuard);          // logical index i lives at XD[pad4(i)], i >= -kGuard
+    double *YD = XD + W.lenP4, *XDD = YD + W.lenP4, *YDD = XDD + W.lenP4;
+    double *NUM = YDD + W.lenP4 - pad4(kGuard) + pad8(kGuard);
+    double *DEN = NUM + W.lenP8;
+    for (int i = lane; i < W.per_warp; i += 32) base[i] = 0.0;   // guard zones (and everything else)
+    const int b = (int)(item / A.nveh);
+    const int v = A.veh_begin + (int)(item - (long long)b * A.nveh);
+    const double *row = A.cpts + ((size_t)b * A.N + v) * A.S;
+    const double val = (double)m / __ldg(A.tf + b);              // diffMatrix(m, tf): m/tf
+    __syncwarp();
+
+    // pos.elev(E)   (bezier.py:469-495)
+    for (int i = lane; i < m1; i += 32) {
+        double sx = 0.0, sy = 0.0;
+        for (int j = 0; j <= n; ++j) {
+            const double t = __ldg(A.Tpos + (size_t)j * m1 + i);
+            sx = fma(__ldg(row + j), t, sx);
+            sy = fma(__ldg(row + n + 1 + j), t, sy);
+        }
+        px[i] = sx;
+        py[i] = sy;
+    }
+    __syncwarp();
+    // first derivatives: np.dot(cpts, Dm) then .elev(1)   (bezier.py:497-519)
+    for (int k = lane; k < m; k += 32) {
+        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
+        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
+    }
+    __syncwarp();
+    for (int k = lane; k < m1; k += 32) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        px[k] = qx;                                  // x', y' (unscaled) reuse px, py
+        py[k] = qy;
+    }
+    __syncwarp();
+    for (int k = lane; k < m; k += 32) {
+        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
+        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
+    }
+    __syncwarp();
+    for (int k = lane; k < m1; k += 32) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k), c = __ldg(A.Cm + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        XDD[pad4(k)] = qx * c;                       // pre-scaled by C(m,k)
+        YDD[pad4(k)] = qy * c;
+        XD[pad4(k)] = px[k] * c;
+        YD[pad4(k)] = py[k] * c;
+    }
+    __syncwarp();
+
+    // ---- phase 1: NUM = y''*x' - x''*y', DEN = x'*x' + y'*y' (pre-scaled by C(2m,k)), R = 4
+    {
+        constexpr int R = 4;
+        const bool active = lane < W.H1;
+        const int j = active ? lane : W.H1 - 1;
+        int k0 = R * j, ioff = 0;
+        double num[R], den[R], wx[R], wy[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            num[r] = 0.0; den[r] = 0.0;
+            wx[r] = XD[pad4(k0 + r)];
+            wy[r] = YD[pad4(k0 + r)];
+        }
+        for (int q = 0; q < W.nseg1; ++q) {
+            if (q == j + 1) {                        // this lane flips to its second tile
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (active && k0 + r < L2) { NUM[pad8(k0 + r)] = num[r]; DEN[pad8(k0 + r)] = den[r]; }
+                k0 = R * (j + W.H1);
+                const int inext = k0 - m1 + 1;
+                ioff = inext - R * q;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    num[r] = 0.0; den[r] = 0.0;
+                    wx[r] = XD[pad4(k0 + r - inext)];
+                    wy[r] = YD[pad4(k0 + r - inext)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int i = R * q + u + ioff;
+                const int ia = pad4(i);
+                const double ydd = YDD[ia], xdd = XDD[ia], xd = XD[ia], yd = YD[ia];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double ax = wx[(r - u) & (R - 1)], ay = wy[(r - u) & (R - 1)];
+                    num[r] = fma(ydd, ax, num[r]);
+                    num[r] = fma(-xdd, ay, num[r]);
+                    den[r] = fma(xd, ax, den[r]);
+                    den[r] = fma(yd, ay, den[r]);
+                }
+                const int iw = pad4(k0 - i - 1);
+                wx[(R - 1 - u) & (R - 1)] = XD[iw];
+                wy[(R - 1 - u) & (R - 1)] = YD[iw];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (active && k0 + r < L2) { NUM[pad8(k0 + r)] = num[r]; DEN[pad8(k0 + r)] = den[r]; }
+    }
+    __syncwarp();
+
+    // ---- phase 2: squares (optimization.py:604,606) and the control-point-wise ratio (:608), R = 8
+    {
+        constexpr int R = 8;
+        double *out = A.out + (size_t)item * L4;
+        const bool active = lane < W.H2;
+        const int j = active ? lane : W.H2 - 1;
+        int k0 = R * j, ioff = 0;
+        double nn[R], dd[R], wn[R], wd[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            nn[r] = 0.0; dd[r] = 0.0;
+            wn[r] = NUM[pad8(k0 + r)];
+            wd[r] = DEN[pad8(k0 + r)];
+        }
+        for (int q = 0; q < W.nseg2; ++q) {
+            if (q == j + 1) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (active && k0 + r < L4) out[k0 + r] = fma(A.alpha, nn[r] / dd[r], A.beta);
+                k0 = R * (j + W.H2);
+                const int inext = k0 - L2 + 1;
+                ioff = inext - R * q;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    nn[r] = 0.0; dd[r] = 0.0;
+                    wn[r] = NUM[pad8(k0 + r - inext)];
+                    wd[r] = DEN[pad8(k0 + r - inext)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int i = R * q + u + ioff;
+                const int ia = pad8(i);
+                const double an = NUM[ia], ad = DEN[ia];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    nn[r] = fma(an, wn[(r - u) & (R - 1)], nn[r]);
+                    dd[r] = fma(ad, wd[(r - u) & (R - 1)], dd[r]);
+                }
+                const int iw = pad8(k0 - i - 1);
+                wn[(R - 1 - u) & (R - 1)] = NUM[iw];
+                wd[(R - 1 - u) & (R - 1)] = DEN[iw];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (active && k0 + r < L4) out[k0 + r] = fma(A.alpha, nn[r] / dd[r], A.beta);
+    }
+}
+
+static WarpPlan make_warp_plan(int m) {
+    WarpPlan W;
+    const int m1 = m + 1, L2 = 2 * m + 1;
+    const int T1 = (2 * m1 - 1 + 3) / 4, T2 = (2 * L2 - 1 + 7) / 8;
+    W.H1 = (T1 + 1) / 2;
+    W.H2 = (T2 + 1) / 2;
+    const int S1 = 2 * m1 + 3 - 4 * W.H1, S2 = 2 * L2 + 7 - 8 * W.H2;
+    W.nseg1 = (S1 + 3) / 4;
+    W.nseg2 = (S2 + 7) / 8;
+    if (W.nseg1 < W.H1) W.nseg1 = W.H1;      // every lane must finish its first tile (R H steps)
+    if (W.nseg2 < W.H2) W.nseg2 = W.H2;
+    auto p4 = [](int i) { return i + (i >> 2); };
+    auto p8 = [](int i) { return i + (i >> 3); };
+    W.lenP4 = p4(kGuard) + p4(m1 + 4 * W.H1 + kGuard) + 2;
+    W.lenP8 = p8(kGuard) + p8(L2 + 8 * W.H2 + kGuard) + 2;
+    W.per_warp = 4 * m1 + 4 * W.lenP4 + 2 * W.lenP8 + 8;
+    W.per_warp = (W.per_warp + 1) / 2 * 2;
+    return W;
+}
+
 }  // namespace
 
 extern "C" int bez_angrate_tables_create(int n, int elev, int device, const double *h_Tpos,
@@ -211,6 +426,22 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
     A.cpts = d_cpts; A.tf = d_tf; A.Tpos = t->d_Tpos; A.lo = t->d_lo; A.hi = t->d_hi;
     A.Cm = t->d_Cm; A.C2m = t->d_C2m; A.out = d_out; A.B = B; A.N = N; A.S = row_stride;
     A.n = t->n; A.m = t->m; A.veh_begin = veh_begin; A.nveh = nveh; A.alpha = alpha; A.beta = beta;
+    // UNVERIFIED on hardware yet: opt-in with BEZGPU_ANGRATE_V2=1 until tools/check_angrate.py has passed
+    const char *use_v2 = getenv("BEZGPU_ANGRATE_V2");
+    if (t->m <= 127 && use_v2 && use_v2[0] == '1') {                  // warp-per-item, tiled and balanced
+        const WarpPlan W = make_warp_plan(t->m);
+        const size_t shw = sizeof(double) * (size_t)W.per_warp * kWarpsW;
+        static size_t attr_w = 0;
+        if (shw > 48 * 1024 && shw > attr_w) {
+            BEZ_CUDA(cudaFuncSetAttribute(angrate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shw));
+            attr_w = shw;
+        }
+        const long long items = (long long)B * nveh;
+        angrate_warp_kernel<<<(unsigned)((items + kWarpsW - 1) / kWarpsW), 32 * kWarpsW, shw,
+                              (cudaStream_t)stream>>>(A, W);
+        BEZ_CUDA(cudaGetLastError());
+        return BEZ_OK;
+    }
     const size_t shmem = sizeof(double) * ((size_t)8 * (t->m + 1) + 2 * (2 * t->m + 1 + 2 * kPad) + kPad);
     static size_t attr_set = 0;
     if (shmem > 48 * 1024 && shmem > attr_set) {
