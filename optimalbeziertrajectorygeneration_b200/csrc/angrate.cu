@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(kAThreads) angrate_kernel(const AngArgs A) {
 // zones of zeros around every row stand in for the ragged ends of the triangle.
 // Requires ceil((4m+1)/8) <= 64, i.e. m <= 127; larger m uses angrate_kernel.
 constexpr int kWarpsW = 4;
-constexpr int kGuard = 16;                      // logical guard on both sides of every padded row
+constexpr int kGuard = 8;                       // logical guard on both sides of every padded row
+                                                // (accessed range: [-4, La+2] for R = 4, [-8, La+6] for R = 8)
 
 __device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
 __device__ __forceinline__ int pad4(int i) { return i + (i >> 2); }
@@ -177,18 +178,20 @@ struct WarpPlan {            // host-computed geometry of the two tiled phases
     int per_warp;            // doubles of shared memory per warp
 };
 
-__global__ void __launch_bounds__(32 * kWarpsW) angrate_warp_kernel(const AngArgs A, const WarpPlan W) {
+__global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp_kernel(const AngArgs A, const WarpPlan W) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long item = (long long)blockIdx.x * kWarpsW + warp;
     if (item >= (long long)A.B * A.nveh) return;                 // whole warp; no block-wide barriers below
     const int m = A.m, n = A.n, m1 = m + 1, L2 = 2 * m + 1, L4 = 4 * m + 1;
     double *base = sm + (size_t)warp * W.per_warp;
-    double *px = base, *py = px + m1, *tmpx = py + m1, *tmpy = tmpx + m1;
-    double *XD = tmpy + m1 + pad4(kGuard);          // logical index i lives at XD[pad4(i)], i >= -kGuard
+    double *XD = base + pad4(kGuard);               // logical index i lives at XD[pad4(i)], i >= -kGuard
     double *YD = XD + W.lenP4, *XDD = YD + W.lenP4, *YDD = XDD + W.lenP4;
     double *NUM = YDD + W.lenP4 - pad4(kGuard) + pad8(kGuard);
     double *DEN = NUM + W.lenP8;
+    // scratch of the derivative steps lives in the interiors of NUM / DEN (2 m + 1 >= 2 (m + 1) - 1
+    // slots each), which phase 1 overwrites completely; the guard zones stay untouched
+    double *px = NUM, *py = NUM + m1, *tmpx = DEN, *tmpy = DEN + m1;
     for (int i = lane; i < W.per_warp; i += 32) base[i] = 0.0;   // guard zones (and everything else)
     const int b = (int)(item / A.nveh);
     const int v = A.veh_begin + (int)(item - (long long)b * A.nveh);
@@ -236,6 +239,9 @@ __global__ void __launch_bounds__(32 * kWarpsW) angrate_warp_kernel(const AngArg
         XD[pad4(k)] = px[k] * c;
         YD[pad4(k)] = py[k] * c;
     }
+    __syncwarp();
+    // the scratch rows are dead: clear the NUM / DEN rows (guards included) for phase 1
+    for (int i = lane; i < 2 * W.lenP8; i += 32) (NUM - pad8(kGuard))[i] = 0.0;
     __syncwarp();
 
     // ---- phase 1: NUM = y''*x' - x''*y', DEN = x'*x' + y'*y' (pre-scaled by C(2m,k)), R = 4
@@ -298,17 +304,22 @@ __global__ void __launch_bounds__(32 * kWarpsW) angrate_warp_kernel(const AngArg
         const int j = active ? lane : W.H2 - 1;
         int k0 = R * j, ioff = 0;
         double nn[R], dd[R], wn[R], wd[R];
+        double nnA[R], ddA[R];                       // results of the first tile, divided at the end
+        const int k0A = k0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            nn[r] = 0.0; dd[r] = 0.0;
+            nn[r] = 0.0; dd[r] = 0.0; nnA[r] = 0.0; ddA[r] = 1.0;
             wn[r] = NUM[pad8(k0 + r)];
             wd[r] = DEN[pad8(k0 + r)];
         }
+        bool flipped = false;
         for (int q = 0; q < W.nseg2; ++q) {
             if (q == j + 1) {
+                // one lane at a time runs this block: keep it short (the divisions wait until
+                // every lane can do them together)
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (active && k0 + r < L4) out[k0 + r] = fma(A.alpha, nn[r] / dd[r], A.beta);
+                for (int r = 0; r < R; ++r) { nnA[r] = nn[r]; ddA[r] = dd[r]; }
+                flipped = true;
                 k0 = R * (j + W.H2);
                 const int inext = k0 - L2 + 1;
                 ioff = inext - R * q;
@@ -334,9 +345,16 @@ __global__ void __launch_bounds__(32 * kWarpsW) angrate_warp_kernel(const AngArg
                 wd[(R - 1 - u) & (R - 1)] = DEN[iw];
             }
         }
+        if (!flipped) {                              // (last lane when the segment count equals H2)
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+            for (int r = 0; r < R; ++r) { nnA[r] = nn[r]; ddA[r] = dd[r]; nn[r] = 0.0; dd[r] = 1.0; }
+            k0 = L4;                                 // nothing to write for a second tile
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (active && k0A + r < L4) out[k0A + r] = fma(A.alpha, nnA[r] / ddA[r], A.beta);
             if (active && k0 + r < L4) out[k0 + r] = fma(A.alpha, nn[r] / dd[r], A.beta);
+        }
     }
 }
 
@@ -353,9 +371,10 @@ static WarpPlan make_warp_plan(int m) {
     if (W.nseg2 < W.H2) W.nseg2 = W.H2;
     auto p4 = [](int i) { return i + (i >> 2); };
     auto p8 = [](int i) { return i + (i >> 3); };
-    W.lenP4 = p4(kGuard) + p4(m1 + 4 * W.H1 + kGuard) + 2;
-    W.lenP8 = p8(kGuard) + p8(L2 + 8 * W.H2 + kGuard) + 2;
-    W.per_warp = 4 * m1 + 4 * W.lenP4 + 2 * W.lenP8 + 8;
+    W.lenP4 = p4(kGuard) + p4(m1 + kGuard) + 2;
+    W.lenP8 = p8(kGuard) + p8(L2 + kGuard) + 2;
+    if (W.lenP8 < p8(kGuard) + 2 * m1 + 2) W.lenP8 = p8(kGuard) + 2 * m1 + 2;   // scratch aliasing
+    W.per_warp = 4 * W.lenP4 + 2 * W.lenP8 + 8;
     W.per_warp = (W.per_warp + 1) / 2 * 2;
     return W;
 }
@@ -426,9 +445,9 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
     A.cpts = d_cpts; A.tf = d_tf; A.Tpos = t->d_Tpos; A.lo = t->d_lo; A.hi = t->d_hi;
     A.Cm = t->d_Cm; A.C2m = t->d_C2m; A.out = d_out; A.B = B; A.N = N; A.S = row_stride;
     A.n = t->n; A.m = t->m; A.veh_begin = veh_begin; A.nveh = nveh; A.alpha = alpha; A.beta = beta;
-    // UNVERIFIED on hardware yet: opt-in with BEZGPU_ANGRATE_V2=1 until tools/check_angrate.py has passed
-    const char *use_v2 = getenv("BEZGPU_ANGRATE_V2");
-    if (t->m <= 127 && use_v2 && use_v2[0] == '1') {                  // warp-per-item, tiled and balanced
+    // BEZGPU_ANGRATE_V1=1 forces the first-generation kernel (A/B runs, tools/check_angrate.py)
+    const char *force_v1 = getenv("BEZGPU_ANGRATE_V1");
+    if (t->m <= 127 && !(force_v1 && force_v1[0] == '1')) {           // warp-per-item, tiled and balanced
         const WarpPlan W = make_warp_plan(t->m);
         const size_t shw = sizeof(double) * (size_t)W.per_warp * kWarpsW;
         static size_t attr_w = 0;

@@ -18,9 +18,9 @@ for deg, E in ((10, 100), (10, 0), (10, 30), (5, 7), (3, 1), (12, 115), (7, 60),
     b = gopt.BezOptimization(**args)
     x = b.generateGuess(std=0.3, seed=deg)
     gopt.DEG_ELEV = E
-    os.environ["BEZGPU_ANGRATE_V2"] = "1"
+    os.environ["BEZGPU_ANGRATE_V1"] = "0"
     new = b.maxAngularRateConstraints(x)
-    os.environ["BEZGPU_ANGRATE_V2"] = "0"
+    os.environ["BEZGPU_ANGRATE_V1"] = "1"
     old = b.maxAngularRateConstraints(x)
     want = O.make_callables(O.Model(**args), E)["angrate"](x)
     e1 = np.abs(new - want).max() / np.abs(want).max()
@@ -29,6 +29,6 @@ for deg, E in ((10, 100), (10, 0), (10, 30), (5, 7), (3, 1), (12, 115), (7, 60),
           (deg, E, deg + E, e1, e2, np.abs(old - want).max() / np.abs(want).max()))
     worst = max(worst, e1)
 gopt.DEG_ELEV = 0
-os.environ["BEZGPU_ANGRATE_V2"] = "0"
+os.environ["BEZGPU_ANGRATE_V1"] = "0"
 assert worst < 1e-9, worst
 print("check_angrate OK, worst %.2e" % worst)
