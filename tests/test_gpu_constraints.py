@@ -207,6 +207,37 @@ def test_c4_full_size_properties(gopt):
     assert changed[touches].mean() > 0.5
 
 
+def test_fused_gather_stores_on_one_gpu(gopt):
+    """bez_pair_sepsq_elev_p2p with 'peer' buffers that live on the same GPU: every minimum
+    lands in the local matrix and in each extra destination (the store path of the fused
+    all-gather; the two-GPU version is tests/test_gpu_multigpu.py)."""
+    import torch
+    from oracle.make_golden import synthetic_swarm_args
+    args, x = synthetic_swarm_args(45)
+    b = gopt.BezOptimization(**args)
+    eng = b._engine(True)
+    X = x[None, :] + np.random.default_rng(9).normal(size=(3, x.size)) * 0.05
+    cpts, _ = eng.assemble(eng.upload(X), 100)
+    P = 45 * 44 // 2
+    local = torch.empty((3, P), dtype=torch.float64, device=eng.device)
+    extra = [torch.full((3, P), float("nan"), dtype=torch.float64, device=eng.device) for _ in range(7)]
+    sep = eng.separation(cpts, 100, 0.9, pairmin=local, peer_ptrs=[t.data_ptr() for t in extra])
+    ref = sep.min(dim=2).values
+    assert torch.equal(local, ref)
+    for t in extra:
+        assert torch.equal(t, ref)
+    with pytest.raises(Exception):                       # more than BEZ_MAX_PEERS destinations
+        eng.separation(cpts, 100, 0.9, pairmin=local, peer_ptrs=[t.data_ptr() for t in extra] + [local.data_ptr()])
+    gopt.DEG_ELEV = 0
+    small = gopt.BezOptimization(numVeh=4, dimension=2, degree=3, initPoints=np.zeros((4, 2)),
+                                 finalPoints=np.ones((4, 2)))
+    e2 = small._engine(True)
+    c2, _ = e2.assemble(e2.upload(np.zeros((1, small.nvar))), 0)
+    with pytest.raises(Exception):                       # L = 7: outside the tensor-path shapes
+        e2.separation(c2, 0, 0.9, pairmin=torch.empty((1, 6), dtype=torch.float64, device=e2.device),
+                      peer_ptrs=[local.data_ptr()])
+
+
 def test_evaluate_sweep_matches_serial_calls(gopt):
     """The pipelined sweep (two workspaces, copy stream) returns what per-chunk
     evaluate_reduced calls return, including a ragged last chunk."""

@@ -155,3 +155,28 @@ def test_fd_jacobian_vs_reference_noise_floor(golden):
         # structural zeros are exact zeros everywhere
         assert np.array_equal(Jref == 0, Jex == 0)
         assert np.array_equal(Jlit == 0, Jex == 0)
+
+
+def test_fd_steps_follow_scipy_rule_for_batches():
+    """engine.fd_steps (host logic, used by batch.ProblemBatch.fd_points for [M, nvar] arrays):
+    h = sqrt(eps) unless x + h == x, dx = (x + h) - x  (scipy/optimize/_numdiff.py:585-596)."""
+    import importlib.util
+    import os
+    import sys
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # engine imports the ctypes binding at import time; only the static helper is needed here
+    src = open(os.path.join(root, "optimalbeziertrajectorygeneration_b200", "engine.py")).read()
+    start = src.index("    @staticmethod\n    def fd_steps")
+    end = src.index("    def _direction_rows")
+    ns = {"np": np}
+    exec("class E:\n" + src[start:end], ns)
+    X = np.array([[0.0, 1.0, -3.5, 1e9, -1e9], [2.5e-9, 7.0, 1e17, -1e17, 5.0]])
+    h, dx = ns["E"].fd_steps(X)
+    assert h.shape == X.shape and dx.shape == X.shape
+    rel = 1.4901161193847656e-08
+    small = np.abs(X) < 1e7
+    assert np.all(h[small] == rel) and np.all(dx[small] == (X[small] + rel) - X[small])
+    assert np.all(dx != 0.0)
+    big = ~small & (np.abs(X) > 1e16)
+    assert np.all(np.abs(h[big]) >= rel * np.abs(X[big]) * 0.999)
