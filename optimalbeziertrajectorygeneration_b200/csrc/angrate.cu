@@ -166,14 +166,15 @@ __global__ void __launch_bounds__(kAThreads) angrate_kernel(const AngArgs A) {
 // zones of zeros around every row stand in for the ragged ends of the triangle.
 // Requires ceil((4m+1)/8) <= 64, i.e. m <= 127; larger m uses angrate_kernel.
 constexpr int kWarpsW = 4;
-constexpr int kGuard = 8;                       // logical guard on both sides of every padded row
-                                                // (accessed range: [-4, La+2] for R = 4, [-8, La+6] for R = 8)
+constexpr int kGuard = 16;                      // logical guard on both sides of every padded row
+                                                // (accessed range, checked for all m <= 127 by emulation:
+                                                //  physical offsets [-9, +14] around the row)
 
 __device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
 __device__ __forceinline__ int pad4(int i) { return i + (i >> 2); }
 
 struct WarpPlan {            // host-computed geometry of the two tiled phases
-    int H1, nseg1, H2, nseg2;
+    int H1, nseg1, e1, H2, nseg2, e2;   // e: phase-B start offset in segments (floor, may be -1)
     int lenP4, lenP8;        // doubles per pad4 / pad8 row (with guards)
     int per_warp;            // doubles of shared memory per warp
 };
@@ -244,18 +245,24 @@ __global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp_kernel(const Ang
     for (int i = lane; i < 2 * W.lenP8; i += 32) (NUM - pad8(kGuard))[i] = 0.0;
     __syncwarp();
 
+    // Addressing: with the phase-B start rounded down to a multiple of R (e1, e2 below; the
+    // extra leading terms hit window zeros) every index of a segment is "multiple of R plus u",
+    // so under the maps i -> i + i/R the loads of a segment are  pointer[+-u]  with one pointer
+    // update per row and segment instead of shift/add index arithmetic per load.
     // ---- phase 1: NUM = y''*x' - x''*y', DEN = x'*x' + y'*y' (pre-scaled by C(2m,k)), R = 4
     {
-        constexpr int R = 4;
+        constexpr int R = 4, P = R + 1;              // P = padded stride of one segment
         const bool active = lane < W.H1;
         const int j = active ? lane : W.H1 - 1;
-        int k0 = R * j, ioff = 0;
+        int k0 = R * j;
         double num[R], den[R], wx[R], wy[R];
+        const double *ax = XD, *ay = YD, *axx = XDD, *ayy = YDD;   // a side: row[P (q + ea) + u]
+        const double *bx = XD + P * j - 2, *by = YD + P * j - 2;   // window:  row[P (jw - q) - 2 - u]
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             num[r] = 0.0; den[r] = 0.0;
-            wx[r] = XD[pad4(k0 + r)];
-            wy[r] = YD[pad4(k0 + r)];
+            wx[r] = bx[2 + r];
+            wy[r] = by[2 + r];
         }
         for (int q = 0; q < W.nseg1; ++q) {
             if (q == j + 1) {                        // this lane flips to its second tile
@@ -263,32 +270,31 @@ __global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp_kernel(const Ang
                 for (int r = 0; r < R; ++r)
                     if (active && k0 + r < L2) { NUM[pad8(k0 + r)] = num[r]; DEN[pad8(k0 + r)] = den[r]; }
                 k0 = R * (j + W.H1);
-                const int inext = k0 - m1 + 1;
-                ioff = inext - R * q;
+                ax += P * W.e1; ay += P * W.e1; axx += P * W.e1; ayy += P * W.e1;
+                bx += P * (W.H1 - W.e1); by += P * (W.H1 - W.e1);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     num[r] = 0.0; den[r] = 0.0;
-                    wx[r] = XD[pad4(k0 + r - inext)];
-                    wy[r] = YD[pad4(k0 + r - inext)];
+                    wx[r] = bx[2 + r];
+                    wy[r] = by[2 + r];
                 }
             }
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                const int i = R * q + u + ioff;
-                const int ia = pad4(i);
-                const double ydd = YDD[ia], xdd = XDD[ia], xd = XD[ia], yd = YD[ia];
+                const double ydd = ayy[u], xdd = axx[u], xd = ax[u], yd = ay[u];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const double ax = wx[(r - u) & (R - 1)], ay = wy[(r - u) & (R - 1)];
-                    num[r] = fma(ydd, ax, num[r]);
-                    num[r] = fma(-xdd, ay, num[r]);
-                    den[r] = fma(xd, ax, den[r]);
-                    den[r] = fma(yd, ay, den[r]);
+                    const double vx = wx[(r - u) & (R - 1)], vy = wy[(r - u) & (R - 1)];
+                    num[r] = fma(ydd, vx, num[r]);
+                    num[r] = fma(-xdd, vy, num[r]);
+                    den[r] = fma(xd, vx, den[r]);
+                    den[r] = fma(yd, vy, den[r]);
                 }
-                const int iw = pad4(k0 - i - 1);
-                wx[(R - 1 - u) & (R - 1)] = XD[iw];
-                wy[(R - 1 - u) & (R - 1)] = YD[iw];
+                wx[(R - 1 - u) & (R - 1)] = bx[-u];
+                wy[(R - 1 - u) & (R - 1)] = by[-u];
             }
+            ax += P; ay += P; axx += P; ayy += P;
+            bx -= P; by -= P;
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -298,19 +304,21 @@ __global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp_kernel(const Ang
 
     // ---- phase 2: squares (optimization.py:604,606) and the control-point-wise ratio (:608), R = 8
     {
-        constexpr int R = 8;
+        constexpr int R = 8, P = R + 1;
         double *out = A.out + (size_t)item * L4;
         const bool active = lane < W.H2;
         const int j = active ? lane : W.H2 - 1;
-        int k0 = R * j, ioff = 0;
+        int k0 = R * j;
         double nn[R], dd[R], wn[R], wd[R];
         double nnA[R], ddA[R];                       // results of the first tile, divided at the end
         const int k0A = k0;
+        const double *an_ = NUM, *ad_ = DEN;
+        const double *bn = NUM + P * j - 2, *bd = DEN + P * j - 2;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             nn[r] = 0.0; dd[r] = 0.0; nnA[r] = 0.0; ddA[r] = 1.0;
-            wn[r] = NUM[pad8(k0 + r)];
-            wd[r] = DEN[pad8(k0 + r)];
+            wn[r] = bn[2 + r];
+            wd[r] = bd[2 + r];
         }
         bool flipped = false;
         for (int q = 0; q < W.nseg2; ++q) {
@@ -321,29 +329,28 @@ __global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp_kernel(const Ang
                 for (int r = 0; r < R; ++r) { nnA[r] = nn[r]; ddA[r] = dd[r]; }
                 flipped = true;
                 k0 = R * (j + W.H2);
-                const int inext = k0 - L2 + 1;
-                ioff = inext - R * q;
+                an_ += P * W.e2; ad_ += P * W.e2;
+                bn += P * (W.H2 - W.e2); bd += P * (W.H2 - W.e2);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     nn[r] = 0.0; dd[r] = 0.0;
-                    wn[r] = NUM[pad8(k0 + r - inext)];
-                    wd[r] = DEN[pad8(k0 + r - inext)];
+                    wn[r] = bn[2 + r];
+                    wd[r] = bd[2 + r];
                 }
             }
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                const int i = R * q + u + ioff;
-                const int ia = pad8(i);
-                const double an = NUM[ia], ad = DEN[ia];
+                const double an = an_[u], ad = ad_[u];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     nn[r] = fma(an, wn[(r - u) & (R - 1)], nn[r]);
                     dd[r] = fma(ad, wd[(r - u) & (R - 1)], dd[r]);
                 }
-                const int iw = pad8(k0 - i - 1);
-                wn[(R - 1 - u) & (R - 1)] = NUM[iw];
-                wd[(R - 1 - u) & (R - 1)] = DEN[iw];
+                wn[(R - 1 - u) & (R - 1)] = bn[-u];
+                wd[(R - 1 - u) & (R - 1)] = bd[-u];
             }
+            an_ += P; ad_ += P;
+            bn -= P; bd -= P;
         }
         if (!flipped) {                              // (last lane when the segment count equals H2)
 #pragma unroll
@@ -364,10 +371,12 @@ static WarpPlan make_warp_plan(int m) {
     const int T1 = (2 * m1 - 1 + 3) / 4, T2 = (2 * L2 - 1 + 7) / 8;
     W.H1 = (T1 + 1) / 2;
     W.H2 = (T2 + 1) / 2;
-    const int S1 = 2 * m1 + 3 - 4 * W.H1, S2 = 2 * L2 + 7 - 8 * W.H2;
-    W.nseg1 = (S1 + 3) / 4;
-    W.nseg2 = (S2 + 7) / 8;
-    if (W.nseg1 < W.H1) W.nseg1 = W.H1;      // every lane must finish its first tile (R H steps)
+    auto floordiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+    W.e1 = floordiv(4 * W.H1 - m1 - 3, 4);          // phase B starts at i = 4 (j + 1 + e1)
+    W.e2 = floordiv(8 * W.H2 - L2 - 7, 8);
+    W.nseg1 = (m1 - 4 * W.e1 + 3) / 4;              // last term i = La - 1 is reached in phase B
+    W.nseg2 = (L2 - 8 * W.e2 + 7) / 8;
+    if (W.nseg1 < W.H1) W.nseg1 = W.H1;             // every lane must finish its first tile (R H steps)
     if (W.nseg2 < W.H2) W.nseg2 = W.H2;
     auto p4 = [](int i) { return i + (i >> 2); };
     auto p8 = [](int i) { return i + (i >> 3); };
