@@ -19,7 +19,7 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
     using namespace bezmma;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t per_warp = (size_t)kRowsDoubles + 16 * (size_t)A.L + 32;
+    const size_t per_warp = (size_t)kRowsDoubles + 16 * (size_t)A.L;
     double *rows = smem + warp * per_warp;
     double *obuf = rows + kRowsDoubles;
     for (int i = lane; i < kRowsDoubles; i += 32) rows[i] = 0.0;     // padding slots must be 0
@@ -74,7 +74,7 @@ int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t s
             PW.w[widx<N_>(i, j)] = (i == j) ? w : 2.0 * w;
         }
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
-    const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L + 32) * sizeof(double);
+    const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L) * sizeof(double);
     auto kern = sq_elev_mma_kernel<N_, DIM, MODE, MINMODE>;
     static size_t attr_set = 0;
     if (shmem > attr_set) {

@@ -226,7 +226,7 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
     using namespace bezmma;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t per_warp = (size_t)kRowsDoubles + 16 * (size_t)A.L + 32;
+    const size_t per_warp = (size_t)kRowsDoubles + 16 * (size_t)A.L;
     double *rows = smem + warp * per_warp;
     double *obuf = rows + kRowsDoubles;
     for (int i = lane; i < kRowsDoubles; i += 32) rows[i] = 0.0;     // padding slots must be 0
@@ -268,7 +268,7 @@ int launch_jac_mma(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
     DiffWeights<N_> DW;
     for (int i = 0; i < (N_ + 1) * (N_ + 1); ++i) FW.w[i] = plan->h_W[i];
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
-    const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L + 32) * sizeof(double);
+    const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L) * sizeof(double);
     auto kern = jac_sq_elev_mma_kernel<N_, DIM, JMODE>;
     static size_t attr_set = 0;
     if (shmem > attr_set) {

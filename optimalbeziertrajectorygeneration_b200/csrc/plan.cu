@@ -70,7 +70,18 @@ extern "C" int bez_plan_create(int n, int dim, int elev, int device,
         }
         PQ[(size_t)n * p->LhPad + i] = h_elevT[(size_t)n * L + i];
     }
-    (void)M;
+    // Padding columns c >= Lh that still lie inside the row (c <= M) get the weights of their
+    // mirror column M - c with the odd part negated: the tensor-path kernels then compute
+    // every one of their LhPad column slots as a *valid* output pair -- slot c yields
+    // (b_c, b_{M-c}) = (mirror, forward) of slot M - c, bit for bit, so the duplicate stores
+    // are benign and no liveness test is needed.  The DFMA kernels ignore columns >= Lh.
+    for (int i = p->Lh; i < p->LhPad; ++i) {
+        const int mi = M - i;
+        if (mi < 0 || mi >= p->Lh) continue;
+        for (int j = 0; j <= n; ++j) PQ[(size_t)j * p->LhPad + i] = PQ[(size_t)j * p->LhPad + mi];
+        for (int j = 0; j < n; ++j)
+            PQ[(size_t)(n + 1 + j) * p->LhPad + i] = -PQ[(size_t)(n + 1 + j) * p->LhPad + mi];
+    }
 
     cudaError_t e;
 #define PLAN_ALLOC_COPY(dst, src, count)                                              \

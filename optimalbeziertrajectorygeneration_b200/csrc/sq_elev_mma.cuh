@@ -79,7 +79,7 @@ __device__ __forceinline__ void load_bfrags(BFrags<N_> &B, const double *__restr
 #pragma unroll
     for (int ni = 0; ni < 8; ++ni) {
         const int col = col_of(ni, g);
-        const bool live = col < Lh;
+        const bool live = col < LhPad;          // columns >= Lh hold mirrored weights (plan.cu): valid duplicates
 #pragma unroll
         for (int ks = 0; ks < Geom<N_>::KE; ++ks) {
             const int j = 4 * ks + t;
@@ -93,28 +93,19 @@ __device__ __forceinline__ void load_bfrags(BFrags<N_> &B, const double *__restr
     }
 }
 
-// Per-lane constants of the epilogue, computed once per kernel.
+// Per-lane constants of the epilogue.
 struct LaneGeom {
     int g, t;
-    unsigned live;      // bit 2 (ni - 4) + c : column 16 (ni >> 1) + 2 (ni & 1) + 4 t + c < Lh  (ni = 4..7)
-    bool live48;        // Lh >= 48: the columns of n-tiles 4, 5 (32..47) are live in every lane
 };
-__device__ __forceinline__ LaneGeom lane_geom(int lane, int Lh) {
+__device__ __forceinline__ LaneGeom lane_geom(int lane, int /*Lh*/) {
     LaneGeom G;
     G.g = lane >> 2;
     G.t = lane & 3;
-    G.live = 0;
-    G.live48 = Lh >= 48;
-#pragma unroll
-    for (int ni = 4; ni < 8; ++ni)
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-            if (16 * (ni >> 1) + 2 * (ni & 1) + 4 * G.t + c < Lh) G.live |= 1u << (2 * (ni - 4) + c);
     return G;
 }
 
 // One warp tile: rows = staged (e,o) rows of 32 items, obuf = 2 x [8][L] doubles of
-// staging (+ 32 doubles of sink for dead columns), obuf_s = its shared-window address,
+// staging, obuf_s = its shared-window address,
 // outg = global address of the tile's first output row (rows contiguous, pitch L),
 // ming = per-item minimum (MINMODE != 0).  seq counts m-tiles over the kernel's
 // lifetime and selects the staging buffer (at most one bulk read is left pending).
@@ -136,7 +127,6 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
     double mnv[4];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) mnv[mi] = INFINITY;
-    double *const sink = obuf + 16 * L + lane;
     const double *ar = rows + g * kRowStride + 4 * t;
     double aE[KE], aO[KO > 0 ? KO : 1];
 #pragma unroll
@@ -174,22 +164,12 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
                 const int cb = 16 * p + 2 * u;              // first column of n-tile 2 p + u
                 const double f0 = c[u][0] + c[u][2], m0 = c[u][0] - c[u][2];
                 const double f1 = c[u][1] + c[u][3], m1 = c[u][1] - c[u][3];
-                bool l0 = true, l1 = true;
-                if (p < 2 || (p == 2 && G.live48)) {        // columns < 32 < Lh (or < 48 <= Lh): always live
-                                                            // (the kernel is bound by in-order issue: skipping the
-                                                            //  selects of one n-tile pair is worth 5 %)
-                    of[cb] = f0; om[-cb] = m0; of[cb + 1] = f1; om[-cb - 1] = m1;
-                } else {                                    // dead columns go to the per-lane sink slot
-                    l0 = (G.live >> (2 * (2 * p + u - 4))) & 1u;
-                    l1 = (G.live >> (2 * (2 * p + u - 4) + 1)) & 1u;
-                    *(l0 ? of + cb : sink) = f0;
-                    *(l0 ? om - cb : sink) = m0;
-                    *(l1 ? of + cb + 1 : sink) = f1;
-                    *(l1 ? om - cb - 1 : sink) = m1;
-                }
+                // every column slot is a valid output pair (slots >= Lh duplicate their mirror
+                // slot bit for bit, see plan.cu), so there is no liveness test on this path
+                of[cb] = f0; om[-cb] = m0; of[cb + 1] = f1; om[-cb - 1] = m1;
                 if (MINMODE) {                              // min(se+so, se-so) = se - |so|, one DADD
-                    cand[u][0] = l0 ? c[u][0] - fabs(c[u][2]) : INFINITY;
-                    cand[u][1] = l1 ? c[u][1] - fabs(c[u][3]) : INFINITY;
+                    cand[u][0] = c[u][0] - fabs(c[u][2]);
+                    cand[u][1] = c[u][1] - fabs(c[u][3]);
                 }
             }
             if (MINMODE) mnp[p] = dmin(dmin(cand[0][0], cand[0][1]), dmin(cand[1][0], cand[1][1]));
