@@ -36,7 +36,7 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
     const long long nwt = (total + 31) >> 5;
     const long long gwarp = (long long)blockIdx.x * kWarps + warp;
     const long long nwarps = (long long)gridDim.x * kWarps;
-    unsigned seq = 0;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(A.out) & 15u) == 0;
 
     for (long long wt = gwarp; wt < nwt; wt += nwarps) {
         const long long g0 = wt << 5;                          // first flattened item of the tile
@@ -57,7 +57,7 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
         }
         __syncwarp();
         mma_tile<N_, MINMODE>(rows, obuf, obuf_s, Bf, G, A.out + (size_t)g0 * A.L, MINMODE ? A.itemmin + g0 : nullptr,
-                               cnt, A.L, A.Lh, A.beta, lane, seq, A.peer_min, MINMODE ? A.npeers : 0, g0);
+                               cnt, A.L, A.Lh, A.beta, lane, base_aligned, A.peer_min, MINMODE ? A.npeers : 0, g0);
         __syncwarp();
     }
     if (lane == 0) bulk_wait_all();      // staging buffers must outlive the last bulk reads

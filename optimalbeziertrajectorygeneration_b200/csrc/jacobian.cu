@@ -238,7 +238,7 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
     const long long nwt = (A.nitems + 31) >> 5;
     const long long gwarp = (long long)blockIdx.x * kWarps + warp;
     const long long nwarps = (long long)gridDim.x * kWarps;
-    unsigned seq = 0;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(A.out) & 15u) == 0;
     for (long long wt = gwarp; wt < nwt; wt += nwarps) {
         const long long t0 = wt << 5;
         const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
@@ -256,7 +256,7 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
             row[slot_e(N_)] = s[N_] * A.scale;
         }
         __syncwarp();
-        mma_tile<N_, 0>(rows, obuf, obuf_s, Bf, G, A.out + (size_t)t0 * A.L, nullptr, cnt, A.L, A.Lh, 0.0, lane, seq);
+        mma_tile<N_, 0>(rows, obuf, obuf_s, Bf, G, A.out + (size_t)t0 * A.L, nullptr, cnt, A.L, A.Lh, 0.0, lane, base_aligned);
         __syncwarp();
     }
     if (lane == 0) bulk_wait_all();

@@ -107,8 +107,9 @@ __device__ __forceinline__ LaneGeom lane_geom(int lane, int /*Lh*/) {
 // One warp tile: rows = staged (e,o) rows of 32 items, obuf = 2 x [8][L] doubles of
 // staging, obuf_s = its shared-window address,
 // outg = global address of the tile's first output row (rows contiguous, pitch L),
-// ming = per-item minimum (MINMODE != 0).  seq counts m-tiles over the kernel's
-// lifetime and selects the staging buffer (at most one bulk read is left pending).
+// ming = per-item minimum (MINMODE != 0).  base_aligned: the output base address is a
+// multiple of 16 bytes (then every full m-tile block is, too).  m-tile mi uses staging
+// buffer mi & 1 (at most one bulk read is left pending).
 //
 // Schedule of one m-tile (8 items): the n-tiles are processed in pairs; the 12 DMMAs of
 // pair p+1 (4 independent accumulator chains, round-robin over the k-steps) are issued
@@ -119,7 +120,7 @@ template <int N_, int MINMODE>
 __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
                                          const BFrags<N_> &B, const LaneGeom &G,
                                          double *__restrict__ outg, double *__restrict__ ming, int cnt,
-                                         int L, int Lh, double beta, int lane, unsigned &seq,
+                                         int L, int Lh, double beta, int lane, bool base_aligned,
                                          double *const *peer_min = nullptr, int npeers = 0, long long peer_off = 0) {
     constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO;
     const int g = G.g, t = G.t;
@@ -137,8 +138,10 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         if (8 * mi >= cnt) break;
-        const unsigned par = seq & 1u;
-        ++seq;
+        // staging buffer mi & 1: every tile but the very last of a launch has 4 m-tiles (the
+        // tiles run over the flattened item list), so the parity is a compile-time constant;
+        // a short tile drains the bulk groups at its end (below)
+        const unsigned par = (unsigned)mi & 1u;
         double *ob = obuf + (size_t)par * 8 * L;
         double *of = ob + g * L + 4 * t;           // forward cursor of this lane (column 4 t of row g)
         double *om = ob + g * L + M - 4 * t;       // mirror cursor
@@ -197,12 +200,16 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
         double *dst = outg + (size_t)8 * mi * L;
         const unsigned bytes = (unsigned)(nrows * L) * 8u;
-        if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
-            if (lane == 0) bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes);
+        if (base_aligned && (nrows == 8 || (bytes & 15u) == 0)) {
+            if (lane == 0) { bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes); bulk_commit(); }
         } else {                                    // odd row count x odd L or unaligned base
             for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
+            if (lane == 0) bulk_commit();           // empty group keeps the count in step
         }
-        if (lane == 0) bulk_commit();               // (possibly empty) group keeps the count in step
+    }
+    if (cnt <= 24) {                                // short tile: realign the buffer rotation
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
     }
     // per-item minima: reduce over the 4 lanes of a row, then lane (g,t) stores item 8 t + g
     if (MINMODE) {
@@ -214,9 +221,11 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         const double v = t == 0 ? mnv[0] : t == 1 ? mnv[1] : t == 2 ? mnv[2] : mnv[3];
         if (8 * t + g < cnt) {
             ming[8 * t + g] = v;
+            if (npeers > 0) {                               // fused all-gather: NVLink peer stores
 #pragma unroll
-            for (int q = 0; q < BEZ_MAX_PEERS; ++q)         // fused all-gather: NVLink peer stores
-                if (q < npeers) peer_min[q][peer_off + 8 * t + g] = v;
+                for (int q = 0; q < BEZ_MAX_PEERS; ++q)
+                    if (q < npeers) peer_min[q][peer_off + 8 * t + g] = v;
+            }
         }
     }
 }
