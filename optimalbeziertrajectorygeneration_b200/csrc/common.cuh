@@ -47,11 +47,14 @@ __host__ __device__ inline long long bez_pair_row_offset(long long i, long long 
     return i * (2 * N - i - 1) / 2;
 }
 
-// Inverse of the above: pair index p -> (i, j), i < j.
+// Inverse of the above: pair index p -> (i, j), i < j.  The row is estimated with a
+// single-precision square root (the fp64 sqrt is a ~30-instruction sequence and this runs
+// once per 32 outputs rows in kernels that are bound by instruction issue) and then fixed up
+// exactly with integer arithmetic, so the result does not depend on the estimate's rounding.
 __device__ inline void bez_pair_decode(long long p, int N, int &i, int &j) {
-    double b = 2.0 * (double)N - 1.0;
-    double disc = b * b - 8.0 * (double)p;
-    int ii = (int)((b - sqrt(disc > 0.0 ? disc : 0.0)) * 0.5);
+    const float b = 2.0f * (float)N - 1.0f;
+    const float disc = (float)((2.0 * (double)N - 1.0) * (2.0 * (double)N - 1.0) - 8.0 * (double)p);
+    int ii = (int)((b - __fsqrt_rn(disc > 0.0f ? disc : 0.0f)) * 0.5f);
     if (ii < 0) ii = 0;
     if (ii > N - 2) ii = N - 2;
     while (ii > 0 && bez_pair_row_offset(ii, N) > p) --ii;
