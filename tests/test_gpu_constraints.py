@@ -339,6 +339,36 @@ def test_jacobian_sweep_layout_matches_dense(gopt):
             assert np.array_equal(JT[k, p * L:(p + 1) * L], sw[k, uu])
 
 
+@pytest.mark.parametrize("deg,E,N,dim", [(10, 100, 9, 3), (6, 60, 7, 2), (12, 41, 5, 3)])
+def test_jacobian_sweep_tensor_path_matches_dense(gopt, deg, E, N, dim):
+    """65 <= L <= 128: the sweep layout runs the DMMA kernel, the dense layout the DFMA kernel;
+    both evaluate the same closed-form quotient (agreement to rounding), and the sweep rows
+    also match the exactly rounded FD quotient of the oracle."""
+    from oracle import bezier_oracle as O
+    rng = np.random.default_rng(100 * deg + N)
+    args = dict(numVeh=N, dimension=dim, degree=deg, minimizeGoal='Euclidean', maxSep=0.7, maxSpeed=4.0,
+                tf=12.0, initPoints=rng.uniform(-5, 5, size=(N, dim)), finalPoints=rng.uniform(-5, 5, size=(N, dim)))
+    b = gopt.BezOptimization(**args)
+    eng = b._engine(True)
+    x = rng.normal(size=b.nvar) * 3
+    JT = eng.jac_separation(x, E, dense=True).cpu().numpy()          # [nvar, P*L]   (DFMA kernel)
+    sw = eng.jac_separation(x, E, dense=False).cpu().numpy()         # [nvar*(N-1), L] (DMMA kernel)
+    L = 2 * deg + E + 1
+    sw = sw.reshape(eng.nvar, N - 1, L)
+    scale = np.abs(JT).max()
+    for k in range(eng.nvar):
+        v = k // (eng.dim * eng.ncols)
+        others = [u for u in range(N) if u != v]
+        for uu, u in enumerate(others):
+            i, j = min(v, u), max(v, u)
+            p = i * (2 * N - i - 1) // 2 + (j - i - 1)
+            assert np.abs(JT[k, p * L:(p + 1) * L] - sw[k, uu]).max() <= 1e-13 * scale
+    # rows that do not depend on the variable are exactly zero in the dense layout
+    gopt.DEG_ELEV = E
+    Jfun = b.temporalSeparationConstraints_jac(x)                    # [m, nvar], public closure
+    assert relerr(Jfun, JT.T) < 1e-15
+
+
 def test_angrate_rejects_3d(gopt):
     from oracle.make_golden import synthetic_swarm_args
     args, x = synthetic_swarm_args(3)
