@@ -255,6 +255,29 @@ def test_evaluate_sweep_matches_serial_calls(gopt):
     assert np.array_equal(sw2["pairmin"], pm[:3])
 
 
+@pytest.mark.parametrize("deg,elev,K", [(3, 10, 37), (10, 100, 70), (5, 0, 1)])
+def test_sequential_swarm_constraint(gopt, deg, elev, K):
+    """Examples/SequentialSwarm.py:43-70: new vehicle vs frozen trajectories, one minimum each."""
+    from oracle import bezier_oracle as O
+    from optimalbeziertrajectorygeneration_b200.sequential import FrozenSwarm
+    rng = np.random.default_rng(deg + K)
+    traj = rng.uniform(0, 100, size=(K, 3, deg + 1))
+    new = rng.uniform(0, 100, size=(4, 3, deg + 1))
+    fs = FrozenSwarm(traj, elev=elev)
+    got = fs.separation_minima(new, 1.0)
+    W, T = O.prod_weights(deg), O.elev_matrix(2 * deg, elev)
+    want = np.empty((4, K))
+    for b in range(4):
+        for i in range(K):
+            a = new[b] - traj[i]
+            G = np.einsum('di,dj->ij', a, a) * W
+            s = 1.5 * np.array([np.trace(G[::-1], offset=k - deg) for k in range(2 * deg + 1)])
+            want[b, i] = (s @ T).min() - 1.0
+    assert relerr(got, want) < RTOL
+    assert np.array_equal(fs.separation_minima(new[2], 1.0), got[2])
+    assert FrozenSwarm(np.zeros((0, 3, deg + 1)), elev=elev).separation_minima(new[0], 1.0).shape == (0,)
+
+
 def test_single_vehicle_returns_none(gopt):
     b = gopt.BezOptimization(numVeh=1, dimension=2, degree=5, initPoints=[(0, 0)], finalPoints=[(1, 1)])
     assert b.temporalSeparationConstraints(np.zeros(b.nvar)) is None
