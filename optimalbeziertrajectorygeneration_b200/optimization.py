@@ -366,14 +366,15 @@ class BezOptimization:
                         'pairmin': torch.empty((chunk, P), dtype=torch.float64, device=eng.device),
                         'maxspeed': torch.empty((chunk, nv, L), dtype=torch.float64, device=eng.device),
                         'done': None}
-            sw = {'key': (chunk, E), 'sets': [wsset(), wsset()], 'copy_stream': torch.cuda.Stream(device=eng.device)}
+            sw = {'key': (chunk, E), 'sets': [wsset(), wsset()], 'copy_stream': torch.cuda.Stream(device=eng.device),
+                  'copy_stream2': torch.cuda.Stream(device=eng.device)}
             self._sweep_ws = sw
         if out is None:
             out = {'pairmin': eng._pinned_buf('sweep_pairmin', M * P).view(M, P),
                    'maxspeed': eng._pinned_buf('sweep_maxspeed', M * nv * L).view(M, nv * L)}
         xs = eng._pinned_buf('sweep_x', X.size).view(M, eng.nvar)
         xs.numpy()[:] = X
-        main, side = torch.cuda.current_stream(), sw['copy_stream']
+        main, side, side2 = torch.cuda.current_stream(), sw['copy_stream'], sw['copy_stream2']
         max_speed2 = float(self.model['maxSpeed']) ** 2
         for k, lo in enumerate(range(0, M, chunk)):
             hi = min(M, lo + chunk)
@@ -387,10 +388,16 @@ class BezOptimization:
             eng.speed(cpts, tf, E, -1.0, max_speed2, nveh=nv, out=ws['maxspeed'][:b])
             ready = torch.cuda.Event()
             ready.record(main)
+            # the two result blocks leave on two copy streams (two copy engines share the link)
+            with torch.cuda.stream(side2):
+                side2.wait_event(ready)
+                out['maxspeed'][lo:hi].copy_(ws['maxspeed'][:b].view(b, -1), non_blocking=True)
+                done2 = torch.cuda.Event()
+                done2.record(side2)
             with torch.cuda.stream(side):
                 side.wait_event(ready)
                 out['pairmin'][lo:hi].copy_(ws['pairmin'][:b], non_blocking=True)
-                out['maxspeed'][lo:hi].copy_(ws['maxspeed'][:b].view(b, -1), non_blocking=True)
+                side.wait_event(done2)
                 ws['done'] = torch.cuda.Event()
                 ws['done'].record(side)
         side.synchronize()
