@@ -365,6 +365,212 @@ __global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp_kernel(const Ang
     }
 }
 
+// ---------------------------------------------------------------------------
+// Third generation: the same balanced tiling, but the two half-warps work on different
+// products so that a lane needs fewer shared-memory loads per DFMA (ncu on the kernel above:
+// L1 data pipe 85 %, fp64 pipe 49 % -- every LDS.64 of a warp moves 256 bytes to the
+// register file whatever its address pattern).
+//   phase 1 (R = 8):  lanes 0..15 NUM = y''*x' + (-x'')*y',  lanes 16..31 DEN = x'*x' + y'*y'
+//                     4 loads : 16 DFMA per step   (was 6 : 16)
+//   phase 2 (R = 16): lanes 0..15 NUM^2,  lanes 16..31 DEN^2
+//                     2 loads : 16 DFMA per step   (was 4 : 16)
+// Lane j of a half owns tiles j and j + H (H <= 16 for m <= 127); the ratio needs one
+// exchange of 16 values with the partner lane (shfl xor 16) at the very end.
+constexpr int kGuard2 = 32;
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+struct WarpPlan2 {
+    int H1, nseg1, e1, H2, nseg2, e2;
+    int lenP8, lenP16;       // doubles per pad8 / pad16 row (with guards)
+    int per_warp;
+};
+
+__global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp2_kernel(const AngArgs A, const WarpPlan2 W) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * kWarpsW + warp;
+    if (item >= (long long)A.B * A.nveh) return;                 // whole warp; no block-wide barriers below
+    const int m = A.m, n = A.n, m1 = m + 1, L2 = 2 * m + 1, L4 = 4 * m + 1;
+    double *base = sm + (size_t)warp * W.per_warp;
+    double *XD = base + pad8(kGuard2);              // logical index i lives at XD[pad8(i)], i >= -kGuard2
+    double *YD = XD + W.lenP8, *XDN = YD + W.lenP8, *YDD = XDN + W.lenP8;      // XDN = -x''
+    double *NUM = YDD + W.lenP8 - pad8(kGuard2) + pad16(kGuard2);              // pad16 rows
+    double *DEN = NUM + W.lenP16;
+    double *px = NUM, *py = NUM + m1, *tmpx = DEN, *tmpy = DEN + m1;           // scratch, cleared below
+    for (int i = lane; i < W.per_warp; i += 32) base[i] = 0.0;
+    const int b = (int)(item / A.nveh);
+    const int v = A.veh_begin + (int)(item - (long long)b * A.nveh);
+    const double *row = A.cpts + ((size_t)b * A.N + v) * A.S;
+    const double val = (double)m / __ldg(A.tf + b);              // diffMatrix(m, tf): m/tf
+    __syncwarp();
+
+    // pos.elev(E)   (bezier.py:469-495)
+    for (int i = lane; i < m1; i += 32) {
+        double sx = 0.0, sy = 0.0;
+        for (int j = 0; j <= n; ++j) {
+            const double t = __ldg(A.Tpos + (size_t)j * m1 + i);
+            sx = fma(__ldg(row + j), t, sx);
+            sy = fma(__ldg(row + n + 1 + j), t, sy);
+        }
+        px[i] = sx;
+        py[i] = sy;
+    }
+    __syncwarp();
+    // first derivatives: np.dot(cpts, Dm) then .elev(1)   (bezier.py:497-519)
+    for (int k = lane; k < m; k += 32) {
+        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
+        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
+    }
+    __syncwarp();
+    for (int k = lane; k < m1; k += 32) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        px[k] = qx;                                  // x', y' (unscaled) reuse px, py
+        py[k] = qy;
+    }
+    __syncwarp();
+    for (int k = lane; k < m; k += 32) {
+        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
+        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
+    }
+    __syncwarp();
+    for (int k = lane; k < m1; k += 32) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k), c = __ldg(A.Cm + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        XDN[pad8(k)] = -(qx * c);                    // pre-scaled by C(m,k); x'' stored negated
+        YDD[pad8(k)] = qy * c;
+        XD[pad8(k)] = px[k] * c;
+        YD[pad8(k)] = py[k] * c;
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * W.lenP16; i += 32) (NUM - pad16(kGuard2))[i] = 0.0;   // scratch rows are dead
+    __syncwarp();
+
+    const int half = lane >> 4, jl = lane & 15;
+    // ---- phase 1 (R = 8): acc_k = sum_i p_i x'_{k-i} + q_i y'_{k-i},  (p, q) = (y'', -x'') or (x', y')
+    {
+        constexpr int R = 8, P = R + 1;
+        const bool active = jl < W.H1;
+        const int j = active ? jl : W.H1 - 1;
+        int k0 = R * j;
+        double acc[R], wx[R], wy[R];
+        const double *ap = half ? XD : YDD, *aq = half ? YD : XDN;          // a side: row[P (q + ea) + u]
+        const double *bx = XD + P * j - 2, *by = YD + P * j - 2;            // window:  row[P (jw - q) - 2 - u]
+        double *dst = half ? DEN : NUM;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[r] = 0.0; wx[r] = bx[2 + r]; wy[r] = by[2 + r]; }
+        for (int q = 0; q < W.nseg1; ++q) {
+            if (q == j + 1) {                        // this lane flips to its second tile
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (active && k0 + r < L2) dst[pad16(k0 + r)] = acc[r];
+                k0 = R * (j + W.H1);
+                ap += P * W.e1; aq += P * W.e1;
+                bx += P * (W.H1 - W.e1); by += P * (W.H1 - W.e1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) { acc[r] = 0.0; wx[r] = bx[2 + r]; wy[r] = by[2 + r]; }
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const double pv = ap[u], qv = aq[u];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    acc[r] = fma(pv, wx[(r - u) & (R - 1)], acc[r]);
+                    acc[r] = fma(qv, wy[(r - u) & (R - 1)], acc[r]);
+                }
+                wx[(R - 1 - u) & (R - 1)] = bx[-u];
+                wy[(R - 1 - u) & (R - 1)] = by[-u];
+            }
+            ap += P; aq += P;
+            bx -= P; by -= P;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (active && k0 + r < L2) dst[pad16(k0 + r)] = acc[r];
+    }
+    __syncwarp();
+
+    // ---- phase 2 (R = 16): squares (optimization.py:604,606); ratio (:608) after one exchange
+    {
+        constexpr int R = 16, P = R + 1;
+        double *out = A.out + (size_t)item * L4;
+        const bool active = jl < W.H2;
+        const int j = active ? jl : W.H2 - 1;
+        int k0 = R * j;
+        const int k0A = k0;
+        double acc[R], w[R], accA[R];
+        const double *src = half ? DEN : NUM;
+        const double *ap = src;
+        const double *bw = src + P * j - 2;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[r] = 0.0; accA[r] = 0.0; w[r] = bw[2 + r]; }
+        bool flipped = false;
+        for (int q = 0; q < W.nseg2; ++q) {
+            if (q == j + 1) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) accA[r] = acc[r];
+                flipped = true;
+                k0 = R * (j + W.H2);
+                ap += P * W.e2;
+                bw += P * (W.H2 - W.e2);
+#pragma unroll
+                for (int r = 0; r < R; ++r) { acc[r] = 0.0; w[r] = bw[2 + r]; }
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const double av = ap[u];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = fma(av, w[(r - u) & (R - 1)], acc[r]);
+                w[(R - 1 - u) & (R - 1)] = bw[-u];
+            }
+            ap += P;
+            bw -= P;
+        }
+        if (!flipped) {                              // (last lane when the segment count equals H2)
+#pragma unroll
+            for (int r = 0; r < R; ++r) { accA[r] = acc[r]; acc[r] = 0.0; }
+            k0 = L4;                                 // no second tile
+        }
+        // half 0 holds NUM^2 (tiles A, B), half 1 DEN^2: half 0 finishes tile A, half 1 tile B
+        const int kB = __shfl_xor_sync(0xffffffffu, k0, 16);       // (equal in both halves)
+        (void)kB;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double other = __shfl_xor_sync(0xffffffffu, half ? accA[r] : acc[r], 16);
+            // half 0: other = DEN^2 of tile A;  half 1: other = NUM^2 of tile B
+            const double nn = half ? other : accA[r];
+            const double dd = half ? acc[r] : other;
+            const int k = (half ? k0 : k0A) + r;
+            if (active && k < L4) out[k] = fma(A.alpha, nn / dd, A.beta);
+        }
+    }
+}
+
+static WarpPlan2 make_warp_plan2(int m) {
+    WarpPlan2 W;
+    const int m1 = m + 1, L2 = 2 * m + 1;
+    const int T1 = (2 * m1 - 1 + 7) / 8, T2 = (2 * L2 - 1 + 15) / 16;
+    W.H1 = (T1 + 1) / 2;
+    W.H2 = (T2 + 1) / 2;
+    auto floordiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+    W.e1 = floordiv(8 * W.H1 - m1 - 7, 8);
+    W.e2 = floordiv(16 * W.H2 - L2 - 15, 16);
+    W.nseg1 = (m1 - 8 * W.e1 + 7) / 8;
+    W.nseg2 = (L2 - 16 * W.e2 + 15) / 16;
+    if (W.nseg1 < W.H1) W.nseg1 = W.H1;
+    if (W.nseg2 < W.H2) W.nseg2 = W.H2;
+    auto p8 = [](int i) { return i + (i >> 3); };
+    auto p16 = [](int i) { return i + (i >> 4); };
+    W.lenP8 = p8(kGuard2) + p8(m1 + kGuard2) + 2;
+    W.lenP16 = p16(kGuard2) + p16(L2 + kGuard2) + 2;
+    if (W.lenP16 < p16(kGuard2) + 2 * m1 + 2) W.lenP16 = p16(kGuard2) + 2 * m1 + 2;   // scratch aliasing
+    W.per_warp = 4 * W.lenP8 + 2 * W.lenP16 + 8;
+    W.per_warp = (W.per_warp + 1) / 2 * 2;
+    return W;
+}
+
 static WarpPlan make_warp_plan(int m) {
     WarpPlan W;
     const int m1 = m + 1, L2 = 2 * m + 1;
@@ -456,6 +662,21 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
     A.n = t->n; A.m = t->m; A.veh_begin = veh_begin; A.nveh = nveh; A.alpha = alpha; A.beta = beta;
     // BEZGPU_ANGRATE_V1=1 forces the first-generation kernel (A/B runs, tools/check_angrate.py)
     const char *force_v1 = getenv("BEZGPU_ANGRATE_V1");
+    const char *gen = getenv("BEZGPU_ANGRATE_GEN");                   // "2": second generation (A/B runs)
+    if (t->m <= 127 && !(force_v1 && force_v1[0] == '1') && !(gen && gen[0] == '2')) {
+        const WarpPlan2 W = make_warp_plan2(t->m);                   // half-warp split, R = 8 / 16
+        const size_t shw = sizeof(double) * (size_t)W.per_warp * kWarpsW;
+        static size_t attr_w2 = 0;
+        if (shw > 48 * 1024 && shw > attr_w2) {
+            BEZ_CUDA(cudaFuncSetAttribute(angrate_warp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shw));
+            attr_w2 = shw;
+        }
+        const long long items = (long long)B * nveh;
+        angrate_warp2_kernel<<<(unsigned)((items + kWarpsW - 1) / kWarpsW), 32 * kWarpsW, shw,
+                               (cudaStream_t)stream>>>(A, W);
+        BEZ_CUDA(cudaGetLastError());
+        return BEZ_OK;
+    }
     if (t->m <= 127 && !(force_v1 && force_v1[0] == '1')) {           // warp-per-item, tiled and balanced
         const WarpPlan W = make_warp_plan(t->m);
         const size_t shw = sizeof(double) * (size_t)W.per_warp * kWarpsW;
