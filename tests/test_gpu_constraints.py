@@ -238,6 +238,29 @@ def test_fused_gather_stores_on_one_gpu(gopt):
                       peer_ptrs=[local.data_ptr()])
 
 
+def test_unaligned_and_ragged_outputs(gopt):
+    """Output base that is only 8-byte aligned (no TMA bulk stores possible) and item counts that
+    leave ragged last tiles / odd row counts: the copy fallback must give the same bits."""
+    import torch
+    from oracle.make_golden import synthetic_swarm_args
+    for N, B, E in ((23, 3, 50), (12, 2, 100), (7, 5, 45)):
+        args, x = synthetic_swarm_args(N)
+        b = gopt.BezOptimization(**args)
+        eng = b._engine(True)
+        X = x[None, :] + np.random.default_rng(N).normal(size=(B, x.size)) * 0.05
+        cpts, _ = eng.assemble(eng.upload(X), E)
+        P, L = N * (N - 1) // 2, 2 * 10 + E + 1
+        ref = eng.separation(cpts, E, 0.9)
+        flat = torch.full((B * P * L + 1,), float("nan"), dtype=torch.float64, device=eng.device)
+        odd = flat[1:].view(B, P, L)
+        assert odd.data_ptr() % 16 == 8
+        pm = torch.empty((B, P), dtype=torch.float64, device=eng.device)
+        eng.separation(cpts, E, 0.9, out=odd, pairmin=pm)
+        assert torch.equal(odd, ref) and torch.equal(pm, ref.min(dim=2).values)
+        part = eng.separation(cpts, E, 0.9, pair_begin=3, npairs=P - 5)      # ragged range
+        assert torch.equal(part, ref[:, 3:P - 2])
+
+
 def test_evaluate_sweep_matches_serial_calls(gopt):
     """The pipelined sweep (two workspaces, copy stream) returns what per-chunk
     evaluate_reduced calls return, including a ragged last chunk."""
