@@ -367,27 +367,51 @@ class BezOptimization:
                         'maxspeed': torch.empty((chunk, nv, L), dtype=torch.float64, device=eng.device),
                         'done': None}
             sw = {'key': (chunk, E), 'sets': [wsset(), wsset()], 'copy_stream': torch.cuda.Stream(device=eng.device),
-                  'copy_stream2': torch.cuda.Stream(device=eng.device)}
+                  'copy_stream2': torch.cuda.Stream(device=eng.device),
+                  'upload_stream': torch.cuda.Stream(device=eng.device)}
             self._sweep_ws = sw
         if out is None:
             out = {'pairmin': eng._pinned_buf('sweep_pairmin', M * P).view(M, P),
                    'maxspeed': eng._pinned_buf('sweep_maxspeed', M * nv * L).view(M, nv * L)}
         xs = eng._pinned_buf('sweep_x', X.size).view(M, eng.nvar)
-        xs.numpy()[:] = X
+        xs_np = xs.numpy()                           # filled chunk by chunk, just ahead of each upload
         main, side, side2 = torch.cuda.current_stream(), sw['copy_stream'], sw['copy_stream2']
+        up = sw['upload_stream']
         max_speed2 = float(self.model['maxSpeed']) ** 2
+
+        def upload(k, after):
+            # x of chunk k goes up one step ahead on its own stream, so that it never queues
+            # behind the result copies of the previous chunk on a shared copy engine
+            lo_ = k * chunk
+            hi_ = min(M, lo_ + chunk)
+            xs_np[lo_:hi_] = X[lo_:hi_]
+            with torch.cuda.stream(up):
+                if after is not None:
+                    up.wait_event(after)             # kernels that last read this set's x
+                sw['sets'][k & 1]['x'][:hi_ - lo_].copy_(xs[lo_:hi_], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+            return ev
+
+        nchunks = (M + chunk - 1) // chunk
+        up.wait_stream(main)
+        x_ready = upload(0, None)
+        prev_ready = None
         for k, lo in enumerate(range(0, M, chunk)):
             hi = min(M, lo + chunk)
             b = hi - lo
             ws = sw['sets'][k & 1]
             if ws['done'] is not None:
                 main.wait_event(ws['done'])          # D2H of the chunk that used this set two steps ago
-            ws['x'][:b].copy_(xs[lo:hi], non_blocking=True)
+            main.wait_event(x_ready)
+            if k + 1 < nchunks:
+                x_ready = upload(k + 1, prev_ready)
             cpts, tf = eng.assemble(ws['x'][:b], E)
             eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b], pairmin=ws['pairmin'][:b])
             eng.speed(cpts, tf, E, -1.0, max_speed2, nveh=nv, out=ws['maxspeed'][:b])
             ready = torch.cuda.Event()
             ready.record(main)
+            prev_ready = ready
             # the two result blocks leave on two copy streams (two copy engines share the link)
             with torch.cuda.stream(side2):
                 side2.wait_event(ready)
