@@ -71,18 +71,22 @@ class ClockSampler:
         self.thread = None
         self.err = None
 
+    def _open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it lists indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.gpu
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            idx = int(vis.split(",")[self.gpu])
+        self._nvml = pynvml
+        self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+
     def _run(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it lists indices
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            idx = self.gpu
-            if vis and all(t.strip().isdigit() for t in vis.split(",")):
-                idx = int(vis.split(",")[self.gpu])
-            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            while not self._stop.is_set():
+            pynvml, h = self._nvml, self._h
+            while True:
                 self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                 try:
                     mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -91,11 +95,18 @@ class ClockSampler:
                 for name, bit in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(self.period)
+                if self._stop.wait(self.period):
+                    break
         except Exception as e:            # pragma: no cover
             self.err = repr(e)
 
     def start(self):
+        # NVML is opened here, before the timed region starts, so that short runs are sampled too
+        try:
+            self._open()
+        except Exception as e:            # pragma: no cover
+            self.err = repr(e)
+            return
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
