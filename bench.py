@@ -299,7 +299,7 @@ def run_ours(opts):
     if gatherer is not None:
         gatherer.finish()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period=opts.clock_period)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -511,7 +511,7 @@ def run_c5(opts):
     for _ in range(max(3, opts.warmup)):
         F = step()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period=opts.clock_period)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -575,6 +575,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="evals (x vectors) per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--clock-period", type=float, default=0.002, help="NVML sampling period in seconds")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="multi-GPU: use the NCCL all-gather instead of the fused in-kernel peer stores")
     ap.add_argument("--no-sweep", action="store_true", help="skip the closed-form Jacobian sweep leg")
