@@ -100,12 +100,18 @@ class ClockSampler:
         except Exception as e:            # pragma: no cover
             self.err = repr(e)
 
-    def start(self):
-        # NVML is opened here, before the timed region starts, so that short runs are sampled too
+    def open(self):
+        """NVML is opened ahead of the timed region (and of the barrier in front of it: it takes
+        milliseconds, on rank 0 only), so that short runs are sampled from their first step."""
         try:
             self._open()
         except Exception as e:            # pragma: no cover
             self.err = repr(e)
+
+    def start(self):
+        if self.err is None and not hasattr(self, "_h"):
+            self.open()
+        if self.err is not None:
             return
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
@@ -298,8 +304,10 @@ def run_ours(opts):
         step()
     if gatherer is not None:
         gatherer.finish()
-    barrier()
     sampler = ClockSampler(local, period=opts.clock_period)
+    if rank == 0:
+        sampler.open()
+    barrier()
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -510,8 +518,10 @@ def run_c5(opts):
 
     for _ in range(max(3, opts.warmup)):
         F = step()
-    barrier()
     sampler = ClockSampler(local, period=opts.clock_period)
+    if rank == 0:
+        sampler.open()
+    barrier()
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
