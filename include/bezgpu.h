@@ -220,6 +220,16 @@ int bez_objective_euclidean(const bez_plan *plan, const double *d_cpts, int B, i
 int bez_objective_accel(const bez_plan *plan, const double *d_cpts, const double *d_tf, int B,
                         int N, int numVeh, double *d_out, void *stream);
 
+/* Gradient of the cost callables as SciPy forms it for SLSQP ('2-point' rule on
+ * objectiveFunction, scipy/optimize/_slsqp_py.py:424-426 -> _numdiff.py:585-596, 683-712):
+ * d_out[k] = (f(x + dx_k e_k) - f(x)) / dx_k for the numVeh*dim*ncols control-point variables
+ * (row-major (vehicle, dimension, free column); free column col = control point col + offset,
+ * optimization.py:242-285), in cancellation-free closed form from the assembled control points
+ * d_cpts [N][S] of the base x.  kind 0 = euclidean (optimization.py:462-489), 1 = accel
+ * (optimization.py:503-519, tf = the model's tf).  Replaces nvar+1 host calls of the callable. */
+int bez_objective_grad(const bez_plan *plan, const double *d_cpts, int kind, double tf, int numVeh,
+                       int ncols, int offset, const double *d_dx, double *d_out, void *stream);
+
 /* ---- A8: Bezier.split -> deCasteljauSplit (bezier.py:533-572, 985-1027), bit exact.
  *   d_cpts [count][dim][n+1]; d_tlocal [count] = (tDiv - t0)/(tf - t0); outputs same shape,
  *   right half already in ascending order (bezier.py:563).  One warp per curve. */

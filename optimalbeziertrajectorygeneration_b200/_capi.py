@@ -55,6 +55,7 @@ SIGNATURES = {
     "bez_curve_eval": (I, [P, P, L64, I, I, D, D, P, P]),
     "bez_objective_euclidean": (I, [c_plan_p, P, I, I, I, P, P]),
     "bez_objective_accel": (I, [c_plan_p, P, P, I, I, I, P, P]),
+    "bez_objective_grad": (I, [c_plan_p, P, I, D, I, I, I, P, P, P]),
     "bez_split": (I, [P, P, I, I, I, P, P, P]),
     "bez_extrema_scratch_doubles": (ctypes.c_size_t, [I, I, I]),
     "bez_extrema": (I, [P, I, I, D, I, I, P, P, P, P]),

@@ -329,7 +329,13 @@ class Bezier(BezierParams):
         c2.tf = self.tf
         return c1, c2
 
-    def _extreme(self, dim, tol, maximum, max_depth=64):
+    def _extreme(self, dim, tol, maximum, glob, max_depth=64):
+        # root call of the recursion: the caller's bound is already within tol of the extreme
+        # control point (bezier.py:651-656 / 747-752)
+        vals = self._f64()[dim]
+        ext = vals.max() if maximum else vals.min()
+        if np.abs(glob - ext) < tol:
+            return float(ext)
         row = _to_dev(self._f64()[dim])
         n = self.deg
         scratch = torch.empty(int(_capi.lib.bez_extrema_scratch_doubles(1, n, max_depth)), dtype=F64,
@@ -338,15 +344,21 @@ class Bezier(BezierParams):
         status = torch.zeros(1, dtype=torch.int32, device=row.device)
         _capi.call("bez_extrema", _ptr(row), 1, n, float(tol), int(maximum), max_depth, _ptr(scratch),
                    _ptr(out), _iptr(status), _stream())
+        self.last_status = int(status.item())
+        if self.last_status != 0:
+            # the subdivision did not converge within max_depth levels; the reference's
+            # recursion has no bound and ends in Python's RecursionError
+            raise RecursionError('Bezier.%s: subdivision depth limit (%d) reached'
+                                 % ('max' if maximum else 'min', max_depth))
         return float(out.item())
 
     def min(self, dim=0, globMin=-np.inf, tol=1e-6):
         """bezier.py:631-667"""
-        return self._extreme(dim, tol, False)
+        return self._extreme(dim, tol, False, globMin)
 
     def max(self, dim=0, globMax=np.inf, tol=1e-6):
         """bezier.py:727-763"""
-        return self._extreme(dim, tol, True)
+        return self._extreme(dim, tol, True, globMax)
 
     # -- distance routines ----------------------------------------------------
     def minDist(self, otherCurve, max_depth=200):
@@ -388,29 +400,21 @@ class RationalBezier(BezierParams):
 
 
 def _temporalAlignment(c1, c2):
-    """bezier.py:903-941"""
-    newC1, newC2 = c1.copy(), c2.copy()
-    if c1.t0 < c2.t0:
-        t0 = c2.t0
-        _, newC1 = newC1.split(t0)
-    elif c1.t0 > c2.t0:
-        t0 = c1.t0
-        _, newC2 = newC2.split(t0)
-    else:
-        t0 = c1.t0
-    if c1.tf < c2.tf:
-        tf = c1.tf
-        newC2, _ = newC2.split(tf)
-    elif c1.tf > c2.tf:
-        tf = c2.tf
-        newC1, _ = newC1.split(tf)
-    else:
-        tf = c1.tf
-    newC1.t0 = t0
-    newC2.t0 = t0
-    newC1.tf = tf
-    newC2.tf = tf
-    return newC1, newC2
+    """Restricts two curves to the time window they share, [max t0, min tf], by
+    subdividing whichever curve sticks out at either end (bezier.py:903-941; used by
+    add/sub when the windows differ)."""
+    t0 = max(c1.t0, c2.t0)
+    tf = min(c1.tf, c2.tf)
+    pieces = []
+    for curve in (c1, c2):
+        piece = curve.copy()
+        if curve.t0 < t0:                 # starts early: keep the part after t0
+            piece = piece.split(t0)[1]
+        if curve.tf > tf:                 # ends late: keep the part before tf
+            piece = piece.split(tf)[0]
+        piece.t0, piece.tf = t0, tf
+        pieces.append(piece)
+    return pieces[0], pieces[1]
 
 
 # ---------------------------------------------------------------------------

@@ -608,7 +608,7 @@ extern "C" int bez_angrate_tables_create(int n, int elev, int device, const doub
         bez_set_error("bez_angrate_tables_create: n+elev = %d > 250 (C(2m,m)^2 would overflow fp64)", m);
         return BEZ_EUNSUPPORTED;
     }
-    BEZ_CUDA(cudaSetDevice(device));
+    BEZ_ON_DEVICE(device);
     bez_angrate_tables *t = (bez_angrate_tables *)calloc(1, sizeof(bez_angrate_tables));
     if (!t) { bez_set_error("out of host memory"); return BEZ_ENOMEM; }
     t->n = n; t->elev = elev; t->m = m; t->device = device;
@@ -655,7 +655,7 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
                 "vehicle range outside [0, N)");
     BEZ_REQUIRE(row_stride >= 2 * (t->n + 1), "control-point rows are not two dimensional");
     if (B == 0 || nveh == 0) return BEZ_OK;
-    BEZ_CUDA(cudaSetDevice(t->device));
+    BEZ_ON_DEVICE(t->device);
     AngArgs A;
     A.cpts = d_cpts; A.tf = d_tf; A.Tpos = t->d_Tpos; A.lo = t->d_lo; A.hi = t->d_hi;
     A.Cm = t->d_Cm; A.C2m = t->d_C2m; A.out = d_out; A.B = B; A.N = N; A.S = row_stride;
@@ -666,11 +666,8 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
     if (t->m <= 127 && !(force_v1 && force_v1[0] == '1') && !(gen && gen[0] == '2')) {
         const WarpPlan2 W = make_warp_plan2(t->m);                   // half-warp split, R = 8 / 16
         const size_t shw = sizeof(double) * (size_t)W.per_warp * kWarpsW;
-        static size_t attr_w2 = 0;
-        if (shw > 48 * 1024 && shw > attr_w2) {
-            BEZ_CUDA(cudaFuncSetAttribute(angrate_warp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shw));
-            attr_w2 = shw;
-        }
+        int sms_ = 0, per_sm_ = 0;
+        if (int rc = bez_kernel_config((const void *)angrate_warp2_kernel, 32 * kWarpsW, shw, &sms_, &per_sm_)) return rc;
         const long long items = (long long)B * nveh;
         angrate_warp2_kernel<<<(unsigned)((items + kWarpsW - 1) / kWarpsW), 32 * kWarpsW, shw,
                                (cudaStream_t)stream>>>(A, W);
@@ -680,11 +677,8 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
     if (t->m <= 127 && !(force_v1 && force_v1[0] == '1')) {           // warp-per-item, tiled and balanced
         const WarpPlan W = make_warp_plan(t->m);
         const size_t shw = sizeof(double) * (size_t)W.per_warp * kWarpsW;
-        static size_t attr_w = 0;
-        if (shw > 48 * 1024 && shw > attr_w) {
-            BEZ_CUDA(cudaFuncSetAttribute(angrate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shw));
-            attr_w = shw;
-        }
+        int sms_ = 0, per_sm_ = 0;
+        if (int rc = bez_kernel_config((const void *)angrate_warp_kernel, 32 * kWarpsW, shw, &sms_, &per_sm_)) return rc;
         const long long items = (long long)B * nveh;
         angrate_warp_kernel<<<(unsigned)((items + kWarpsW - 1) / kWarpsW), 32 * kWarpsW, shw,
                               (cudaStream_t)stream>>>(A, W);
@@ -692,11 +686,8 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
         return BEZ_OK;
     }
     const size_t shmem = sizeof(double) * ((size_t)8 * (t->m + 1) + 2 * (2 * t->m + 1 + 2 * kPad) + kPad);
-    static size_t attr_set = 0;
-    if (shmem > 48 * 1024 && shmem > attr_set) {
-        BEZ_CUDA(cudaFuncSetAttribute(angrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        attr_set = shmem;
-    }
+    int sms_ = 0, per_sm_ = 0;
+    if (int rc = bez_kernel_config((const void *)angrate_kernel, kAThreads, shmem, &sms_, &per_sm_)) return rc;
     angrate_kernel<<<(unsigned)((long long)B * nveh), kAThreads, shmem, (cudaStream_t)stream>>>(A);
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;

@@ -34,6 +34,35 @@ int bez_cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return bez_cuda_fail(e__, #call); \
     } while (0)
 
+// Entry points run on the device their plan / tables live on and restore the caller's current
+// device on return (a host thread that drives several GPUs must not find its device changed).
+struct BezDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit BezDeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            switched = (err == cudaSuccess);
+        }
+    }
+    ~BezDeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    BezDeviceGuard(const BezDeviceGuard &) = delete;
+    BezDeviceGuard &operator=(const BezDeviceGuard &) = delete;
+};
+#define BEZ_ON_DEVICE(device)                                                     \
+    BezDeviceGuard bez_guard__(device);                                            \
+    if (bez_guard__.err != cudaSuccess) return bez_cuda_fail(bez_guard__.err, "cudaSetDevice")
+
+// Launch configuration of a kernel on the *current* device, cached per (kernel, device, shared
+// memory size) behind a mutex: opts the kernel in to `shmem` bytes of dynamic shared memory on
+// that device (the attribute is per device) and returns the SM count and the resident CTAs per
+// SM.  plan.cu.
+int bez_kernel_config(const void *func, int threads, size_t shmem, int *sms, int *ctas_per_sm);
+
 #define BEZ_REQUIRE(cond, msg)                 \
     do {                                       \
         if (!(cond)) {                         \

@@ -177,16 +177,8 @@ int launch_sq_elev2(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) 
         return BEZ_EUNSUPPORTED;
     }
     auto kern = sq_elev_kernel<N_, DIM, MODE, CPL, WITH_MIN>;
-    static size_t attr_set = 0;       // per template instantiation
-    if (shmem > attr_set) {
-        BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        attr_set = shmem;
-    }
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
-    if (per_sm < 1) per_sm = 1;
+    int sms = 148, per_sm = 1;
+    if (int rc = bez_kernel_config((const void *)kern, kThreads, shmem, &sms, &per_sm)) return rc;
     const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
     long long grid = (long long)sms * per_sm;
     const long long need = (nwt + kWarps - 1) / kWarps;
@@ -254,7 +246,7 @@ extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, i
     BEZ_REQUIRE(pair_begin >= 0 && npairs >= 0 && pair_begin + npairs <= (P > 0 ? P : 0),
                 "pair range outside the N(N-1)/2 list");
     if (B == 0 || npairs == 0) return BEZ_OK;
-    BEZ_CUDA(cudaSetDevice(plan->device));
+    BEZ_ON_DEVICE(plan->device);
     SqElevArgs A;
     A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = d_pairmin;
     A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
@@ -280,7 +272,7 @@ extern "C" int bez_pair_sepsq_elev_p2p(const bez_plan *plan, const double *d_cpt
         return BEZ_EUNSUPPORTED;
     }
     if (B == 0 || npairs == 0) return BEZ_OK;
-    BEZ_CUDA(cudaSetDevice(plan->device));
+    BEZ_ON_DEVICE(plan->device);
     SqElevArgs A;
     A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = d_pairmin;
     A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
@@ -298,7 +290,7 @@ extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, con
     BEZ_REQUIRE(B >= 0 && N >= 0 && veh_begin >= 0 && nveh >= 0 && veh_begin + nveh <= N,
                 "vehicle range outside [0, N)");
     if (B == 0 || nveh == 0) return BEZ_OK;
-    BEZ_CUDA(cudaSetDevice(plan->device));
+    BEZ_ON_DEVICE(plan->device);
     SqElevArgs A;
     A.cpts = d_cpts; A.tf = d_tf; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = nullptr;
     A.item_begin = veh_begin; A.nitems = nveh; A.B = B; A.N = N;
@@ -345,7 +337,7 @@ extern "C" int bez_assemble_cpts_sets(const bez_plan *plan, const double *d_x, i
     BEZ_REQUIRE(ncols >= 0, "degree too small for the fixed columns");
     BEZ_REQUIRE(nvar == numVeh * plan->dim * ncols + (timeopt ? 1 : 0), "nvar does not match the model");
     if (B == 0) return BEZ_OK;
-    BEZ_CUDA(cudaSetDevice(plan->device));
+    BEZ_ON_DEVICE(plan->device);
     AssembleArgs A;
     A.x = d_x; A.B = B; A.nvar = nvar; A.numVeh = numVeh; A.nObs = nObs; A.n = plan->n;
     A.dim = plan->dim; A.fixed_ends = fixed_ends; A.dubins = dubins; A.timeopt = timeopt;

@@ -76,16 +76,8 @@ int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t s
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
     const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L) * sizeof(double);
     auto kern = sq_elev_mma_kernel<N_, DIM, MODE, MINMODE>;
-    static size_t attr_set = 0;
-    if (shmem > attr_set) {
-        BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        attr_set = shmem;
-    }
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
-    if (per_sm < 1) per_sm = 1;
+    int sms = 148, per_sm = 1;
+    if (int rc = bez_kernel_config((const void *)kern, kThreads, shmem, &sms, &per_sm)) return rc;
     const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
     long long grid = (long long)sms * per_sm;
     const long long need = (nwt + kWarps - 1) / kWarps;

@@ -154,6 +154,85 @@ __global__ void accel_kernel(const double *cpts, const double *tf, const double 
     if (threadIdx.x == 0) out[blockIdx.x] = tot;
 }
 
+// Gradient of the cost callables as SciPy's '2-point' rule defines it (the objective analogue
+// of jacobian.cu): g_k = (f(x + dx_k e_k) - f(x)) / dx_k, evaluated without cancellation.
+// Variable k = (vehicle v, dimension d, free column col) moves control point c = col + offset of
+// row d by dx_k and nothing else (fixed-tf models: the cost callables that depend on control
+// points are never used with a tf variable).  One thread per variable; cpts [N][S] of the base x.
+//   euclid: only the two polygon segments at c change; |a + dx e_d| - |a| = dx (2 a_d + dx) / (|a + dx e_d| + |a|)
+//   accel : f is a quadratic form of the control points, acc(P + dx e) = acc(P) + dx acc(e):
+//           quotient = sum_k rs_k (dim/2) sum_{i+j=k} W_ij (2 a_i u_j + dx u_i u_j),  u = acc(e_c)
+__global__ void euclid_grad_kernel(const double *cpts, int S, int dim, int n1, int ncols, int offset,
+                                   const double *dx, int nvar, double *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nvar) return;
+    const int col = k % ncols, vd = k / ncols, d = vd % dim, v = vd / dim;
+    const int c = col + offset;
+    const double *p = cpts + (size_t)v * S;
+    const double h = dx[k];
+    double acc = 0.0;
+    for (int side = 0; side < 2; ++side) {
+        // side 0: segment (c-1 -> c), a = P_c - P_{c-1}, moves by +h e_d
+        // side 1: segment (c -> c+1), a = P_{c+1} - P_c, moves by -h e_d
+        const int lo = side == 0 ? c - 1 : c;
+        if (lo < 0 || lo + 1 >= n1) continue;
+        const double sh = side == 0 ? h : -h;
+        double q0 = 0.0, q1 = 0.0, ad = 0.0;
+        for (int j = 0; j < dim; ++j) {
+            const double t = p[j * n1 + lo + 1] - p[j * n1 + lo];
+            const double t1 = (j == d) ? t + sh : t;
+            if (j == d) ad = t;
+            q0 = fma(t, t, q0);
+            q1 = fma(t1, t1, q1);
+        }
+        const double den = sqrt(q1) + sqrt(q0);
+        acc += den > 0.0 ? sh * (2.0 * ad + sh) / den : fabs(sh);
+    }
+    out[k] = acc / h;
+}
+
+__global__ void accel_grad_kernel(const double *cpts, double tf, const double *W, const double *E1,
+                                  const double *T, int S, int dim, int n1, int L, int ncols, int offset,
+                                  const double *dx, int nvar, double *out) {
+    extern __shared__ double rs[];                      // row sums of elevMatrix(2n, E)
+    const int n = n1 - 1;
+    for (int r = threadIdx.x; r <= 2 * n; r += blockDim.x) {
+        double t = 0.0;
+        for (int i = 0; i < L; ++i) t += T[(size_t)r * L + i];
+        rs[r] = t;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nvar) return;
+    const int col = k % ncols, vd = k / ncols, d = vd % dim, v = vd / dim;
+    const int c = col + offset;
+    const double val = (double)n / tf;
+    double a[32], u[32], q[32];
+    for (int i = 0; i < n1; ++i) { a[i] = cpts[(size_t)v * S + d * n1 + i]; u[i] = (i == c) ? 1.0 : 0.0; }
+    for (int which = 0; which < 2; ++which) {
+        double *p = which == 0 ? a : u;
+        for (int rep = 0; rep < 2; ++rep) {              // Bezier.diff twice (Q3: degree kept)
+            for (int i = 0; i < n1; ++i) {
+                double r = 0.0;
+                if (i < n) r = (p[i] * (-val) + p[i + 1] * val) * E1[(size_t)i * n1 + i];
+                if (i > 0) r = (p[i - 1] * (-val) + p[i] * val) * E1[(size_t)(i - 1) * n1 + i] + r;
+                q[i] = r;
+            }
+            for (int i = 0; i < n1; ++i) p[i] = q[i];
+        }
+    }
+    const double h = dx[k];
+    double acc = 0.0;
+    for (int kk = 0; kk <= 2 * n; ++kk) {
+        const int ilo = kk - n > 0 ? kk - n : 0, ihi = kk < n ? kk : n;
+        double s = 0.0;
+        for (int i = ilo; i <= ihi; ++i)
+            s = fma(W[(size_t)i * n1 + (kk - i)], fma(h * u[i], u[kk - i], 2.0 * a[i] * u[kk - i]), s);
+        acc = fma((s * (double)dim) / 2.0, rs[kk], acc);
+    }
+    out[k] = acc;
+}
+
 inline unsigned blocks_for(long long total) {
     long long b = (total + 255) / 256;
     if (b > 148 * 32) b = 148 * 32;
@@ -225,6 +304,29 @@ extern "C" int bez_objective_accel(const bez_plan *plan, const double *d_cpts, c
     const int n1 = plan->n + 1, S = (plan->dim * n1 + 1) / 2 * 2;
     accel_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(d_cpts, d_tf, plan->d_W, plan->d_E1, plan->d_T, N, S,
                                                      numVeh, plan->dim, n1, plan->L, d_out);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
+
+extern "C" int bez_objective_grad(const bez_plan *plan, const double *d_cpts, int kind, double tf, int numVeh,
+                                  int ncols, int offset, const double *d_dx, double *d_out, void *stream) {
+    BEZ_REQUIRE(plan && d_cpts && d_dx && d_out, "NULL argument");
+    BEZ_REQUIRE(numVeh >= 1 && ncols >= 0 && offset >= 0 && ncols + 2 * offset == plan->n + 1,
+                "free columns + fixed end columns must add up to degree + 1");
+    BEZ_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (euclidean) or 1 (accel)");
+    const int n1 = plan->n + 1, S = (plan->dim * n1 + 1) / 2 * 2;
+    const int nvar = numVeh * plan->dim * ncols;
+    if (nvar == 0) return BEZ_OK;
+    BEZ_ON_DEVICE(plan->device);
+    const unsigned blocks = (unsigned)((nvar + 127) / 128);
+    if (kind == 0) {
+        euclid_grad_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(d_cpts, S, plan->dim, n1, ncols, offset, d_dx,
+                                                                      nvar, d_out);
+    } else {
+        BEZ_REQUIRE(tf != 0.0, "tf must be non-zero");
+        accel_grad_kernel<<<blocks, 128, sizeof(double) * (2 * plan->n + 1), (cudaStream_t)stream>>>(
+            d_cpts, tf, plan->d_W, plan->d_E1, plan->d_T, S, plan->dim, n1, plan->L, ncols, offset, d_dx, nvar, d_out);
+    }
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;
 }

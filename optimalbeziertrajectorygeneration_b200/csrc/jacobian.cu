@@ -270,16 +270,8 @@ int launch_jac_mma(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
     const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L) * sizeof(double);
     auto kern = jac_sq_elev_mma_kernel<N_, DIM, JMODE>;
-    static size_t attr_set = 0;
-    if (shmem > attr_set) {
-        BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        attr_set = shmem;
-    }
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
-    if (per_sm < 1) per_sm = 1;
+    int sms = 148, per_sm = 1;
+    if (int rc = bez_kernel_config((const void *)kern, kThreads, shmem, &sms, &per_sm)) return rc;
     const long long nwt = (A.nitems + 31) / 32;
     long long grid = (long long)sms * per_sm;
     const long long need = (nwt + kWarps - 1) / kWarps;
@@ -304,16 +296,8 @@ int launch_jac(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
         return BEZ_EUNSUPPORTED;
     }
     auto kern = jac_sq_elev_kernel<N_, DIM, JMODE>;
-    static size_t attr_set = 0;
-    if (shmem > attr_set) {
-        BEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        attr_set = shmem;
-    }
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, shmem));
-    if (per_sm < 1) per_sm = 1;
+    int sms = 148, per_sm = 1;
+    if (int rc = bez_kernel_config((const void *)kern, kThreads, shmem, &sms, &per_sm)) return rc;
     const long long nwt = (A.nitems + 31) / 32;
     long long grid = (long long)sms * per_sm;
     const long long need = (nwt + kWarps - 1) / kWarps;
@@ -428,7 +412,7 @@ extern "C" int bez_jac_sepsq_elev(const bez_plan *plan, const double *d_cpts, in
     const long long P = (long long)N * (N - 1) / 2;
     const long long nvarN = (long long)numVeh * plan->dim * ncols;
     BEZ_REQUIRE(!dense || ld >= P * plan->L, "ld smaller than the constraint block");
-    BEZ_CUDA(cudaSetDevice(plan->device));
+    BEZ_ON_DEVICE(plan->device);
     cudaStream_t st = (cudaStream_t)stream;
     JacArgs A;
     fill_common(plan, A, d_cpts, d_dir, d_dx, N, numVeh, ncols, offset, kdir, dense, d_out, ld);
@@ -459,7 +443,7 @@ extern "C" int bez_jac_speed_sq_elev(const bez_plan *plan, const double *d_cpts,
     BEZ_REQUIRE(kdir < 0 || d_dir, "direction rows are NULL");
     const long long nvarN = (long long)numVeh * plan->dim * ncols;
     BEZ_REQUIRE(!dense || ld >= (long long)numVeh * plan->L, "ld smaller than the constraint block");
-    BEZ_CUDA(cudaSetDevice(plan->device));
+    BEZ_ON_DEVICE(plan->device);
     cudaStream_t st = (cudaStream_t)stream;
     JacArgs A;
     fill_common(plan, A, d_cpts, d_dir, d_dx, N, numVeh, ncols, offset, kdir, dense, d_out, ld);

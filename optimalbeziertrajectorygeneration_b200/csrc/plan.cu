@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -21,6 +22,41 @@ int bez_cuda_fail(cudaError_t e, const char *what) {
 }
 
 extern "C" const char *bez_last_error(void) { return g_err; }
+
+// See common.cuh.  The dynamic-shared-memory opt-in is a per-device function attribute and this
+// library may be driven from several host threads / for several devices of one process.
+namespace {
+struct KernelConfig {
+    const void *func;
+    int device, threads;
+    size_t shmem;
+    int sms, per_sm;
+};
+std::mutex g_cfg_mutex;
+std::vector<KernelConfig> g_cfg;
+}  // namespace
+
+int bez_kernel_config(const void *func, int threads, size_t shmem, int *sms, int *ctas_per_sm) {
+    int dev = 0;
+    BEZ_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    for (const KernelConfig &c : g_cfg)
+        if (c.func == func && c.device == dev && c.threads == threads && c.shmem == shmem) {
+            *sms = c.sms;
+            *ctas_per_sm = c.per_sm;
+            return BEZ_OK;
+        }
+    KernelConfig c{func, dev, threads, shmem, 148, 1};
+    if (shmem > 48 * 1024)
+        BEZ_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    BEZ_CUDA(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+    BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, func, threads, shmem));
+    if (c.per_sm < 1) c.per_sm = 1;
+    g_cfg.push_back(c);
+    *sms = c.sms;
+    *ctas_per_sm = c.per_sm;
+    return BEZ_OK;
+}
 extern "C" int bez_version(void) { return 100; }
 
 extern "C" int bez_plan_create(int n, int dim, int elev, int device,
@@ -36,7 +72,7 @@ extern "C" int bez_plan_create(int n, int dim, int elev, int device,
         return BEZ_EUNSUPPORTED;
     }
     BEZ_REQUIRE(h_elev1 != nullptr, "elev1 table is NULL");
-    BEZ_CUDA(cudaSetDevice(device));
+    BEZ_ON_DEVICE(device);
 
     bez_plan *p = (bez_plan *)calloc(1, sizeof(bez_plan));
     if (!p) {

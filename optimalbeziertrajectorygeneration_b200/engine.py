@@ -25,8 +25,20 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """Raw handle of torch's current stream on ``device`` (default: the current device)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_buffer(t, shape, what):
+    """Caller-supplied device workspaces are handed to the kernels as raw pointers: a wrong
+    size, dtype, layout or device would be an out-of-bounds device write."""
+    if t is None:
+        return
+    if not isinstance(t, torch.Tensor) or t.dtype != F64 or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError("%s must be a contiguous float64 CUDA tensor" % what)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %r, expected %r" % (what, tuple(t.shape), tuple(shape)))
 
 
 class Plan:
@@ -111,6 +123,21 @@ def num_pairs(N):
     return N * (N - 1) // 2
 
 
+def _on_device(method):
+    """Runs an engine method with the engine's device current (entry points without a plan,
+    torch allocations and stream lookups all follow the current device), so an engine built
+    with ``device=k`` works whatever device the calling thread has selected."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == self.dev_index:
+            return method(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return method(self, *a, **k)
+    return wrapper
+
+
 class ConstraintEngine:
     """Everything a BezOptimization model needs on the device.
 
@@ -154,6 +181,18 @@ class ConstraintEngine:
             self.d_ispeed = self.d_fspeed = self.d_icos = self.d_isin = self.d_fcos = self.d_fsin = None
         self.d_obst = dev(obst[:, :self.dim]) if self.nObs else None
         self._pinned = {}
+        self._x_stage = [None, None]        # rotating pinned staging buffers of upload()
+        self._x_event = [None, None]
+        self._x_turn = 0
+
+    def _st(self):
+        """Launch stream: torch's current stream on the engine's own device."""
+        return _stream(self.device)
+
+    def _check(self, t, shape, what):
+        _check_buffer(t, shape, what)
+        if t is not None and t.device != self.device:
+            raise ValueError("%s lives on %s, the engine on %s" % (what, t.device, self.device))
 
     # -- plans -----------------------------------------------------------
     def plan(self, elev):
@@ -167,28 +206,47 @@ class ConstraintEngine:
             self._pinned[key] = buf
         return buf[:numel]
 
+    @_on_device
     def upload(self, X):
         """host float64 [B, nvar] -> device tensor, through pinned memory."""
         X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
         if X.shape[1] != self.nvar:
             raise ValueError("x has %d entries, the model expects %d" % (X.shape[1], self.nvar))
-        stage = self._pinned_buf("x", X.size)
+        # two staging buffers in rotation; a buffer is rewritten only after the H2D copy that
+        # last read it has completed (event), so back-to-back uploads never race an in-flight DMA
+        i = self._x_turn
+        self._x_turn ^= 1
+        if self._x_event[i] is not None:
+            self._x_event[i].synchronize()
+        stage = self._x_stage[i]
+        if stage is None or stage.numel() < X.size:
+            stage = self._x_stage[i] = torch.empty(max(X.size, 1), dtype=F64, pin_memory=True)
+        stage = stage[:X.size]
         stage.numpy()[:] = X.ravel()
         d = torch.empty(X.shape, dtype=F64, device=self.device)
-        d.view(-1).copy_(stage, non_blocking=True)
+        st = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            d.view(-1).copy_(stage, non_blocking=True)
+            ev = self._x_event[i] = torch.cuda.Event()
+            ev.record(st)
         return d
 
+    @_on_device
     def download(self, t, key="out", copy=True):
         """device tensor -> host numpy array (one sync).  With copy=False the
-        returned array aliases the pinned staging buffer and is only valid
-        until the next download with the same key."""
+        returned array aliases the pinned staging buffer named ``key`` and is only valid
+        until the next download with the same key (the closures of BezOptimization use
+        one key each, so results of different closures never alias)."""
         stage = self._pinned_buf(key, t.numel())
-        stage.copy_(t.reshape(-1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        st = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            stage.copy_(t.reshape(-1), non_blocking=True)
+        st.synchronize()
         host = stage.numpy().reshape(tuple(t.shape))
         return host.copy() if copy else host
 
     # -- A0 -----------------------------------------------------------------
+    @_on_device
     def assemble(self, d_x, elev=0, obst_sets=None, evals_per_set=0):
         """reshapeVector (+ obstacle rows) for every row of d_x [B, nvar].
         Returns (cpts [B, N, S], tf [B]) with S = dim*(n+1) rounded up to even.
@@ -207,10 +265,11 @@ class ConstraintEngine:
                    _ptr(self.d_init), _ptr(self.d_final), _ptr(self.d_ispeed), _ptr(self.d_fspeed),
                    _ptr(self.d_icos), _ptr(self.d_isin), _ptr(self.d_fcos), _ptr(self.d_fsin),
                    _ptr(self.d_obst if obst_sets is None else obst_sets),
-                   int(evals_per_set) if obst_sets is not None else 0, _ptr(cpts), _ptr(tf), _stream())
+                   int(evals_per_set) if obst_sets is not None else 0, _ptr(cpts), _ptr(tf), self._st())
         return cpts, tf
 
     # -- A1-A4 --------------------------------------------------------------
+    @_on_device
     def separation(self, cpts, elev, max_sep, pair_begin=0, npairs=None, out=None, pairmin=None,
                    n_curves=None, peer_ptrs=None):
         """Fused sub -> normSquare -> elev -> -maxSep^2 over a range of the
@@ -222,21 +281,31 @@ class ConstraintEngine:
         N = int(cpts.shape[1]) if n_curves is None else int(n_curves)
         if npairs is None:
             npairs = num_pairs(N) - pair_begin
+        if pair_begin < 0 or npairs < 0 or pair_begin + npairs > num_pairs(N):
+            raise ValueError("pair range [%d, %d) outside the %d pairs" % (pair_begin, pair_begin + npairs, num_pairs(N)))
+        self._check(cpts, (B, int(cpts.shape[1]), self.row_stride), "cpts")
         if out is None:
             out = torch.empty((B, npairs, plan.L), dtype=F64, device=self.device)
+        self._check(out, (B, npairs, plan.L), "out")
+        self._check(pairmin, (B, npairs), "pairmin")
         if peer_ptrs:
             if pairmin is None:
                 raise ValueError("peer_ptrs needs the local pairmin destination")
+            if pair_begin != 0 or npairs != num_pairs(N):
+                # the kernel addresses the peers' matrices with the same [B, npairs] pitch as the
+                # local one: a sub-range would land in the wrong rows
+                raise ValueError("peer_ptrs needs the full pair list (pair_begin = 0, npairs = P)")
             arr = (ctypes.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
             _capi.call("bez_pair_sepsq_elev_p2p", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
                        float(max_sep) ** 2, _ptr(out), _ptr(pairmin), ctypes.addressof(arr), len(peer_ptrs),
-                       _stream())
+                       self._st())
             return out
         _capi.call("bez_pair_sepsq_elev", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
-                   float(max_sep) ** 2, _ptr(out), _ptr(pairmin), _stream())
+                   float(max_sep) ** 2, _ptr(out), _ptr(pairmin), self._st())
         return out
 
     # -- A5 -------------------------------------------------------------------
+    @_on_device
     def speed(self, cpts, tf, elev, alpha, beta, veh_begin=0, nveh=None, out=None):
         plan = self.plan(elev)
         B = int(cpts.shape[0])
@@ -245,11 +314,15 @@ class ConstraintEngine:
             nveh = self.numVeh - veh_begin
         if out is None:
             out = torch.empty((B, nveh, plan.L), dtype=F64, device=self.device)
+        self._check(cpts, (B, N, self.row_stride), "cpts")
+        self._check(tf, (B,), "tf")
+        self._check(out, (B, nveh, plan.L), "out")
         _capi.call("bez_speed_sq_elev", plan.handle, _ptr(cpts), _ptr(tf), B, N, int(veh_begin),
-                   int(nveh), float(alpha), float(beta), _ptr(out), _stream())
+                   int(nveh), float(alpha), float(beta), _ptr(out), self._st())
         return out
 
     # -- A6 -------------------------------------------------------------------
+    @_on_device
     def angrate(self, cpts, tf, elev, alpha, beta, veh_begin=0, nveh=None, out=None):
         """alpha * (squared angular rate control points) + beta, [B, nveh, 4(n+E)+1]."""
         if self.dim != 2:
@@ -262,8 +335,11 @@ class ConstraintEngine:
         L4 = 4 * (self.n + int(elev)) + 1
         if out is None:
             out = torch.empty((B, nveh, L4), dtype=F64, device=self.device)
+        self._check(cpts, (B, N, self.row_stride), "cpts")
+        self._check(tf, (B,), "tf")
+        self._check(out, (B, nveh, L4), "out")
         _capi.call("bez_angrate_sq", tabs.handle, _ptr(cpts), _ptr(tf), B, N, self.row_stride,
-                   int(veh_begin), int(nveh), float(alpha), float(beta), _ptr(out), _stream())
+                   int(veh_begin), int(nveh), float(alpha), float(beta), _ptr(out), self._st())
         return out
 
     # -- A7 ---------------------------------------------------------------------
@@ -295,6 +371,7 @@ class ConstraintEngine:
             self._dir = D
         return self._dir
 
+    @_on_device
     def jac_separation(self, x, elev, dense=True, out=None):
         """FD Jacobian of the separation block at x (host vector).
         dense: returns J^T as a device tensor [nvar, P*L]; else the sweep layout.
@@ -321,9 +398,10 @@ class ConstraintEngine:
                 raise ValueError("out must be a contiguous float64 tensor of shape %r" % (shape,))
             ld = 0
         _capi.call("bez_jac_sepsq_elev", plan.handle, _ptr(cpts), self.N, self.numVeh, self.ncols,
-                   self.offset, _ptr(d_dx), _ptr(dirs), kdir, int(dense), _ptr(out), ld, _stream())
+                   self.offset, _ptr(d_dx), _ptr(dirs), kdir, int(dense), _ptr(out), ld, self._st())
         return out
 
+    @_on_device
     def jac_speed(self, x, elev, alpha, dense=True):
         plan = self.plan(elev)
         x = np.asarray(x, dtype=np.float64)
@@ -345,9 +423,10 @@ class ConstraintEngine:
             ld = 0
         _capi.call("bez_jac_speed_sq_elev", plan.handle, _ptr(cpts), self.N, self.numVeh, self.ncols,
                    self.offset, tf, float(alpha), _ptr(d_dx), _ptr(dirs), kdir, int(dense), _ptr(out),
-                   ld, _stream())
+                   ld, self._st())
         return out
 
+    @_on_device
     def jac_angrate(self, x, elev, alpha, beta):
         """Literal '2-point' FD Jacobian of the angular-rate block: base point and
         all nvar perturbed points are evaluated in one batched launch (what SciPy
@@ -363,5 +442,5 @@ class ConstraintEngine:
         m = int(F.shape[1])
         d_dx = torch.as_tensor(dx, device=self.device)
         JT = torch.empty((self.nvar, m), dtype=F64, device=self.device)
-        _capi.call("bez_fd_quotient", _ptr(F), _ptr(d_dx), self.nvar, m, _ptr(JT), _stream())
+        _capi.call("bez_fd_quotient", _ptr(F), _ptr(d_dx), self.nvar, m, _ptr(JT), self._st())
         return JT

@@ -74,15 +74,34 @@ class BezOptimization:
                       'finalAngs': np.atleast_1d(finalAngs),
                       'tf': tf}
         self._device = device
-        # additive: when True the closures return views of the pinned staging
-        # buffer (valid until the next call of the same closure) instead of copies
+        # additive: when True the closures return views of a pinned staging buffer
+        # (one buffer per closure: valid until the next call of the *same* closure)
+        # instead of copies
         self.zero_copy_results = False
         self._engines = {}
 
     # ------------------------------------------------------------------
+    def _model_signature(self):
+        """What the device state was built from.  The reference re-reads ``model`` and
+        ``pointObstacles`` on every call; here the engine is rebuilt when an entry is
+        *replaced* (identity / scalar value changes).  In-place edits of the arrays inside
+        are not seen: call :meth:`invalidate` after those."""
+        m = self.model
+        po = self.pointObstacles
+        return (m['numVeh'], m['dim'], m['deg'], str(m['minGoal']).lower(), float(m['tf']),
+                id(m['initPoints']), id(m['finalPoints']), id(m['initSpeeds']), id(m['finalSpeeds']),
+                id(m['initAngs']), id(m['finalAngs']), id(po), None if po is None else len(po))
+
+    def invalidate(self):
+        """Drops the cached device state (after in-place edits of model arrays / obstacles)."""
+        self._engines = {}
+
     def _engine(self, with_obstacles):
         """Device state; built lazily so constructing a model needs no GPU."""
         key = bool(with_obstacles) and self.pointObstacles is not None
+        sig = self._model_signature()
+        if getattr(self, '_engines_sig', None) != sig:
+            self._engines, self._engines_sig = {}, sig
         eng = self._engines.get(key)
         if eng is None:
             eng = _engine.ConstraintEngine(self.model, self.pointObstacles if key else None,
@@ -124,31 +143,125 @@ class BezOptimization:
             E = _deg_elev()
             cpts, _ = eng.assemble(eng.upload(x), E)
             out = eng.separation(cpts, E, self.model['maxSep'])
-            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+            return eng.download(out, key="out:sep", copy=not self.zero_copy_results).reshape(-1)
         return wrapper
+
+    # -- A13 ---------------------------------------------------------------
+    # Budgets of the bounded branch-and-bound (the reference recurses without bound, Q6) and
+    # what to do with a pair that exhausts them: 'raise' (default) raises RecursionError, which
+    # is what the reference does on such a pair under Python's default recursion limit;
+    # 'nan' returns NaN rows and leaves the per-pair status in ``last_status``.
+    spatial_max_depth = 200
+    spatial_max_nodes = 1 << 18
+    spatial_on_limit = 'raise'
+
+    def _spatial_shapes(self):
+        """Shape obstacles as arrays: ('curve', cpts [dim, n+1]) for Bezier objects (what the
+        reference accepts) and, additively, ('poly', vertices [m, 3]) for convex polytopes
+        given as [m, 2 or 3] vertex arrays (routed through minDist2Poly, bezier.py:1411-1496)."""
+        shapes = []
+        for obstacle in (self.shapeObstacles or []):
+            if hasattr(obstacle, 'cpts'):
+                shapes.append(('curve', np.ascontiguousarray(obstacle.cpts, dtype=np.float64)))
+            else:
+                v = np.asarray(obstacle, dtype=np.float64)
+                if v.ndim != 2 or v.shape[1] not in (2, 3):
+                    raise TypeError('shape obstacles must be Bezier curves or [m, 2|3] vertex arrays')
+                if v.shape[1] == 2:
+                    v = np.hstack([v, np.zeros((v.shape[0], 1))])
+                shapes.append(('poly', np.ascontiguousarray(v)))
+        return shapes
+
+    def _spatial_rows(self, Y):
+        """Y [B, numVeh*dim, deg+1] control-point matrices -> (rows [B, npairs, 3], status
+        [B, npairs]): minDist of every pair i<j among vehicles + shape obstacles, one launch per
+        group of pairs of equal (kind, shape) -- mixed degrees / dimensions and polytopes form
+        their own groups.  Pairs that do not contain a vehicle are computed for b = 0 only."""
+        from . import bezier as _bez
+        numVeh, dim = self.model['numVeh'], self.model['dim']
+        B = Y.shape[0]
+        shapes = self._spatial_shapes()
+        nobj = numVeh + len(shapes)
+        pairs = [(i, j) for i in range(nobj) for j in range(i + 1, nobj)]
+        rows = np.empty((B, len(pairs), 3))
+        status = np.zeros((B, len(pairs)), dtype=np.int32)
+
+        def obj(b, i):
+            if i < numVeh:
+                return 'curve', np.ascontiguousarray(Y[b, i * dim:(i + 1) * dim, :])
+            return shapes[i - numVeh]
+
+        groups = {}
+        for k, (i, j) in enumerate(pairs):
+            for b in range(B if i < numVeh else 1):
+                (ka, a), (kb, c) = obj(b, i), obj(b, j)
+                if ka == 'poly' and kb == 'curve':
+                    (ka, a), (kb, c) = (kb, c), (ka, a)
+                groups.setdefault((ka, kb, a.shape, c.shape), []).append((b, k, a, c))
+        for (ka, kb, _, _), items in groups.items():
+            A = np.stack([it[2] for it in items])
+            C = np.stack([it[3] for it in items])
+            if ka == 'curve' and kb == 'curve':
+                out, st = _bez.min_dist_batch(A, C, max_depth=self.spatial_max_depth,
+                                              max_nodes=self.spatial_max_nodes)
+            elif ka == 'curve':
+                o5, st = _bez.min_dist2poly_batch(A, C, max_depth=self.spatial_max_depth,
+                                                  max_nodes=self.spatial_max_nodes)
+                # (alpha, t1, closest point) has no second curve parameter: the third column
+                # repeats alpha (a duplicate of the distance constraint)
+                out = np.stack([o5[:, 0], o5[:, 1], o5[:, 0]], axis=1)
+                st = st & ~2                   # bit 2 only says "no closest point reported"
+            else:
+                from .gjk import gjk as _gjk
+                flag, _, _, d = _gjk.gjk_batch(A, C)
+                alpha = np.where(flag > 0, d, 0.0)
+                out = np.stack([alpha, alpha, alpha], axis=1)
+                st = np.where(flag < 0, 8, 0).astype(np.int32)
+            for (b, k, _, _), o, s in zip(items, out, st):
+                rows[b, k], status[b, k] = o, s
+        for k, (i, j) in enumerate(pairs):
+            if i >= numVeh:
+                rows[1:, k], status[1:, k] = rows[0, k], status[0, k]
+        return rows, status
+
+    def _spatial_check(self, status):
+        self.last_status = status
+        bad = int((status != 0).sum())
+        if bad and self.spatial_on_limit == 'raise':
+            raise RecursionError('minDist exceeded its depth/node budget on %d of %d pairs (status codes '
+                                 'in last_status); the reference recurses without bound on such pairs '
+                                 '(SURVEY Q6). Set spatial_on_limit = "nan" to get NaN rows instead.'
+                                 % (bad, status.size))
 
     def spatialSeparationConstraints(self, x):
         """optimization.py:109-133: all pairs among the vehicles and the shape
-        obstacles (Bezier objects), minDist - maxSep; like the reference the
-        (alpha, t1, t2) tuple is kept, so the result is [npairs, 3].
-        All pairs run in one launch (one warp per pair)."""
-        from . import bezier as _bez
-        numVeh = self.model['numVeh']
-        dim = self.model['dim']
-        maxSep = self.model['maxSep']
+        obstacles, minDist - maxSep; like the reference the (alpha, t1, t2) tuple is
+        kept, so the result is [npairs, 3].  One warp per pair, one launch
+        per group of equally shaped pairs."""
         y = self.reshapeVector(x)
-        curves = [np.ascontiguousarray(y[i * dim:(i + 1) * dim, :]) for i in range(numVeh)]
-        for obstacle in (self.shapeObstacles or []):
-            curves.append(np.ascontiguousarray(obstacle.cpts, dtype=np.float64))
-        n = len(curves)
-        shapes = {c.shape for c in curves}
-        if len(shapes) != 1:
-            raise ValueError('all vehicles and shape obstacles must share dimension and degree')
-        A = np.stack([curves[i] for i in range(n) for j in range(i + 1, n)])
-        Bc = np.stack([curves[j] for i in range(n) for j in range(i + 1, n)])
-        out, status = _bez.min_dist_batch(A, Bc, max_nodes=1 << 18)
-        self.last_status = status
-        return out - maxSep
+        rows, status = self._spatial_rows(y[None])
+        self._spatial_check(status[0])
+        return rows[0] - self.model['maxSep']
+
+    def spatialSeparationConstraints_jac(self, x):
+        """Additive: the '2-point' FD Jacobian SLSQP would form from nvar+1 calls of
+        spatialSeparationConstraints, [npairs*3, nvar]: the base point and all perturbed
+        points go through the minDist kernel in ONE launch per pair group ((nvar+1) x pairs
+        warps); obstacle-obstacle rows are constants (zero rows)."""
+        x = np.asarray(x, dtype=np.float64)
+        eng = self._engine(with_obstacles=False)
+        h, dx = eng.fd_steps(x)
+        X = np.repeat(x[None, :], x.size + 1, axis=0)
+        idx = np.arange(x.size)
+        X[idx + 1, idx] = x + h
+        cpts, _ = eng.assemble(eng.upload(X), 0)
+        nrow = self.model['dim'] * (self.model['deg'] + 1)
+        Y = eng.download(cpts[:, :, :nrow].contiguous(), key="spatial_y")
+        Y = Y.reshape(x.size + 1, self.model['numVeh'] * self.model['dim'], self.model['deg'] + 1)
+        rows, status = self._spatial_rows(Y)
+        self._spatial_check(status)
+        F = rows.reshape(x.size + 1, -1)
+        return ((F[1:] - F[0]) / dx[:, None]).T
 
     @property
     def minSpeedConstraints(self):
@@ -158,7 +271,7 @@ class BezOptimization:
             E = _deg_elev()
             cpts, tf = eng.assemble(eng.upload(x), E)
             out = eng.speed(cpts, tf, E, 1.0, -float(self.model['minSpeed']) ** 2)
-            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+            return eng.download(out, key="out:minspeed", copy=not self.zero_copy_results).reshape(-1)
         return wrapper
 
     @property
@@ -169,7 +282,7 @@ class BezOptimization:
             E = _deg_elev()
             cpts, tf = eng.assemble(eng.upload(x), E)
             out = eng.speed(cpts, tf, E, -1.0, float(self.model['maxSpeed']) ** 2)
-            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+            return eng.download(out, key="out:maxspeed", copy=not self.zero_copy_results).reshape(-1)
         return wrapper
 
     @property
@@ -184,7 +297,7 @@ class BezOptimization:
             E = _deg_elev()
             cpts, tf = eng.assemble(eng.upload(x), E)
             out = eng.angrate(cpts, tf, E, -1.0, float(self.model['maxAngRate']) ** 2)
-            return eng.download(out, copy=not self.zero_copy_results).reshape(-1)
+            return eng.download(out, key="out:angrate", copy=not self.zero_copy_results).reshape(-1)
         return wrapper
 
     # ------------------------------------------------------------------
@@ -198,7 +311,7 @@ class BezOptimization:
             if eng.N <= 1:
                 return None
             JT = eng.jac_separation(x, _deg_elev(), dense=True)
-            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+            return eng.download(JT, key="jac:sep", copy=not self.zero_copy_results).T
         return wrapper
 
     @property
@@ -206,7 +319,7 @@ class BezOptimization:
         def wrapper(x):
             eng = self._engine(with_obstacles=False)
             JT = eng.jac_speed(x, _deg_elev(), -1.0, dense=True)
-            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+            return eng.download(JT, key="jac:maxspeed", copy=not self.zero_copy_results).T
         return wrapper
 
     @property
@@ -214,7 +327,7 @@ class BezOptimization:
         def wrapper(x):
             eng = self._engine(with_obstacles=False)
             JT = eng.jac_speed(x, _deg_elev(), 1.0, dense=True)
-            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+            return eng.download(JT, key="jac:minspeed", copy=not self.zero_copy_results).T
         return wrapper
 
     @property
@@ -224,50 +337,42 @@ class BezOptimization:
         def wrapper(x):
             eng = self._engine(with_obstacles=False)
             JT = eng.jac_angrate(x, _deg_elev(), -1.0, float(self.model['maxAngRate']) ** 2)
-            return eng.download(JT, key="jac", copy=not self.zero_copy_results).T
+            return eng.download(JT, key="jac:angrate", copy=not self.zero_copy_results).T
         return wrapper
 
     # ------------------------------------------------------------------
     def generateGuess(self, std=0, seed=None):
-        """optimization.py:189-240 (host logic; uses numpy's global RNG like
-        the reference so seeded guesses are identical)."""
-        dim = self.model['dim']
-        deg = self.model['deg']
-        numVeh = self.model['numVeh']
-        tf = self.model['tf']
-        initPoints = self.model['initPoints']
-        finalPoints = self.model['finalPoints']
-        initSpeeds = self.model['initSpeeds']
-        finalSpeeds = self.model['finalSpeeds']
-        initAngs = self.model['initAngs']
-        finalAngs = self.model['finalAngs']
-
+        """Initial guess of optimization.py:189-240 (host logic): per vehicle the straight
+        line between its end points -- for Dubins models between the second and the
+        penultimate control point, which the end speeds and headings pin -- sampled at the
+        free control points, plus N(0, std) noise.  numpy's global RNG is seeded and drawn
+        from in the reference's order (vehicle-major, one draw of a full row per
+        dimension), so seeded guesses are identical."""
+        m = self.model
+        deg, dim, tf = m['deg'], m['dim'], m['tf']
+        dubins = m['initSpeeds'][0] is not None
+        if dubins and dim != 2:
+            raise ValueError('The dimension must be 2 for initial and final speeds and angles.')
+        npts = deg - 1 if dubins else deg + 1
         np.random.seed(seed)
-        xGuess = []
-        for i in range(numVeh):
-            for j in range(dim):
-                if initSpeeds[0] is None:
-                    line = np.linspace(initPoints[i, j], finalPoints[i, j], deg + 1)
-                    line += np.random.randn(deg + 1) * std
-                else:
-                    if dim != 2:
-                        err = ('The dimension must be 2 for initial and final '
-                               'speeds and angles.')
-                        raise ValueError(err)
-                    initMag = initSpeeds[i] * tf / deg
-                    finalMag = finalSpeeds[i] * tf / deg
-                    if j % 2 == 0:
-                        initPt = initPoints[i, j] + initMag * np.cos(initAngs[i])
-                        finalPt = finalPoints[i, j] - finalMag * np.cos(finalAngs[i])
-                    else:
-                        initPt = initPoints[i, j] + initMag * np.sin(initAngs[i])
-                        finalPt = finalPoints[i, j] - finalMag * np.sin(finalAngs[i])
-                    line = np.linspace(initPt, finalPt, deg + 1 - 2)
-                    line += np.random.randn(deg + 1 - 2) * std
-                xGuess.append(line[1:-1])
-        if self.model['minGoal'].lower() == 'timeopt':
-            xGuess.append([tf])
-        return np.concatenate(xGuess)
+        rows = []
+        for veh in range(m['numVeh']):
+            first = [m['initPoints'][veh, axis] for axis in range(dim)]
+            last = [m['finalPoints'][veh, axis] for axis in range(dim)]
+            if dubins:
+                lead_in = m['initSpeeds'][veh] * tf / deg
+                lead_out = m['finalSpeeds'][veh] * tf / deg
+                heading_in = (np.cos(m['initAngs'][veh]), np.sin(m['initAngs'][veh]))
+                heading_out = (np.cos(m['finalAngs'][veh]), np.sin(m['finalAngs'][veh]))
+                first = [first[axis] + lead_in * heading_in[axis] for axis in range(dim)]
+                last = [last[axis] - lead_out * heading_out[axis] for axis in range(dim)]
+            for axis in range(dim):
+                row = np.linspace(first[axis], last[axis], npts)
+                row += np.random.randn(npts) * std
+                rows.append(row[1:-1])
+        if m['minGoal'].lower() == 'timeopt':
+            rows.append([tf])
+        return np.concatenate(rows)
 
     def reshapeVector(self, x):
         """optimization.py:242-285, evaluated by the device assemble kernel
@@ -431,21 +536,65 @@ class BezOptimization:
 
     # -- cost callables (A14, optimization.py:287-308) -----------------------
     def _objective(self, x, kind):
+        """One launch for every row of x: a 1-D x gives a float (the reference's
+        callable), a 2-D batch [B, nvar] gives float64[B]."""
         eng = self._engine(with_obstacles=False)
         E = _deg_elev()
+        single = np.ndim(x) == 1
         d_x = eng.upload(x)
         cpts, tf = eng.assemble(d_x, E)
         out = torch.empty((d_x.shape[0],), dtype=torch.float64, device=eng.device)
         plan = eng.plan(E)
         if kind == 'euclidean':
             _engine._capi.call("bez_objective_euclidean", plan.handle, _engine._ptr(cpts), int(d_x.shape[0]),
-                               eng.N, eng.numVeh, _engine._ptr(out), _engine._stream())
+                               eng.N, eng.numVeh, _engine._ptr(out), eng._st())
         else:
             # the reference passes model['tf'] here even for time-optimal problems
             tfm = torch.full_like(tf, float(self.model['tf']))
             _engine._capi.call("bez_objective_accel", plan.handle, _engine._ptr(cpts), _engine._ptr(tfm),
-                               int(d_x.shape[0]), eng.N, eng.numVeh, _engine._ptr(out), _engine._stream())
-        return float(out[0].item())
+                               int(d_x.shape[0]), eng.N, eng.numVeh, _engine._ptr(out), eng._st())
+        host = eng.download(out, key="out:objective")
+        return float(host[0]) if single else host
+
+    def _objective_grad(self, x, kind):
+        """SciPy's '2-point' gradient of the objective (what SLSQP forms with nvar+1 calls,
+        _slsqp_py.py:424-426) in one launch, cancellation free (bez_objective_grad)."""
+        eng = self._engine(with_obstacles=False)
+        E = _deg_elev()
+        x = np.asarray(x, dtype=np.float64)
+        _, dx = eng.fd_steps(x)
+        nvarN = eng.numVeh * eng.dim * eng.ncols
+        grad = np.zeros(x.size)
+        if nvarN:
+            cpts, _ = eng.assemble(eng.upload(x), E)
+            d_dx = torch.as_tensor(dx[:nvarN], device=eng.device)
+            out = torch.empty((nvarN,), dtype=torch.float64, device=eng.device)
+            _engine._capi.call("bez_objective_grad", eng.plan(E).handle, _engine._ptr(cpts),
+                               0 if kind == 'euclidean' else 1, float(self.model['tf']), eng.numVeh, eng.ncols,
+                               eng.offset, _engine._ptr(d_dx), _engine._ptr(out), eng._st())
+            grad[:nvarN] = eng.download(out, key="out:objective_grad")
+        # a tf variable (time-optimal models) does not enter these two objectives: the
+        # reference evaluates them with model['tf'] and the end-speed control points of a
+        # Dubins model follow x[-1], which Euclidean/Accel models do not have
+        return grad
+
+    @property
+    def objectiveFunction_jac(self):
+        """Additive: gradient of :attr:`objectiveFunction` for ``minimize(jac=...)``, equal to
+        SciPy's own 2-point finite difference of the callable (exactly rounded quotient)."""
+        minGoal = self.model['minGoal'].lower()
+        if minGoal == 'euclidean':
+            return lambda x: self._objective_grad(x, 'euclidean')
+        if minGoal == 'accel':
+            return lambda x: self._objective_grad(x, 'accel')
+        if minGoal == 'timeopt':
+            def grad(x):                 # ((x[-1] + h) - x[-1]) / dx = 1 exactly
+                g = np.zeros(np.size(x))
+                g[-1] = 1.0
+                return g
+            return grad
+        self.objectiveFunction          # raises the reference's ValueError for unknown goals
+        raise NotImplementedError("no gradient for the %r objective" % minGoal)
 
     def euclideanObjective(self, x):
         """optimization.py:287-292 -> _euclideanObjective (:462-489)"""

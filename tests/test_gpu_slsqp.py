@@ -59,6 +59,7 @@ def test_example1_slsqp(with_jac):
         cons[1]['jac'] = bezopt.maxSpeedConstraints_jac
         cons[2]['jac'] = bezopt.maxAngularRateConstraints_jac
     res = sop.minimize(bezopt.objectiveFunction, x0=x0, method='SLSQP', constraints=cons,
+                       jac=bezopt.objectiveFunction_jac if with_jac else None,
                        options={'maxiter': 250, 'disp': False})
     assert res.success
     assert res.fun == pytest.approx(2.4276431891903045, rel=2e-5)
