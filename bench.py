@@ -304,6 +304,8 @@ def run_ours(opts):
         step()
     if gatherer is not None:
         gatherer.finish()
+    if peer is not None:
+        peer.wait()
     sampler = ClockSampler(local, period=opts.clock_period)
     if rank == 0:
         sampler.open()
@@ -316,6 +318,8 @@ def run_ours(opts):
         gathered = step()
     if gatherer is not None:
         gatherer.finish()
+    if peer is not None:
+        peer.wait()                 # the last step's barrier (side stream) is part of the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)

@@ -118,11 +118,46 @@ int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, int B, int N
  * to this rank's block; peer access / symmetric memory is set up by the caller).  The
  * data is complete on a peer once this kernel has finished on every rank (stream-ordered
  * barrier by the caller).  BEZ_EUNSUPPORTED for shapes outside the tensor-path kernels. */
-#define BEZ_MAX_PEERS 7
 int bez_pair_sepsq_elev_p2p(const bez_plan *plan, const double *d_cpts, int B, int N,
                             int64_t pair_begin, int64_t npairs, double maxSep2,
                             double *d_out, double *d_pairmin,
                             const uint64_t *h_peer_min, int npeers, void *stream);
+
+/* Reduced results of the two fused kernels (all device pointers, all optional; NULL = not
+ * produced).  An "item" is a pair (bez_pair_sepsq_elev_ex) or a vehicle (bez_speed_sq_elev_ex);
+ * f = b * nitems + item is its flattened index in the launch.  The quantity reduced is the
+ * minimum over the item's L elevated values -- what Examples/SequentialSwarm.py:62-67 takes
+ * (`.cpts.min()`) and whose sign is the active-constraint flag.
+ *   itemmin     [B][min_pitch] minima (min_pitch = 0 means nitems; a larger pitch lets ranks
+ *               that own pair sub-ranges write into one [B][P] matrix)
+ *   peer_min    host array of npeers <= BEZ_MAX_PEERS device addresses: the same matrix on
+ *               other GPUs (NVLink peer / symmetric memory), each already offset like itemmin;
+ *               every minimum is also stored there from inside the kernel (fused all-gather)
+ *   active_mask bit (f & 31) of word f >> 5 is set iff min < threshold; ceil(B*nitems/32) words
+ *   list_*      compacted list of the items with min < threshold: *list_count (zeroed by the
+ *               caller) receives their number; entry k < list_cap holds list_idx[k] = f and
+ *               list_val[k] = min (order unspecified; entries beyond list_cap are dropped but
+ *               counted, so list_count > list_cap reports the overflow)
+ * With d_out == NULL the pair kernel writes no rows at all (minima only). */
+#define BEZ_MAX_PEERS 7
+typedef struct bez_reduce_opts {
+    double *itemmin;
+    int64_t min_pitch;
+    const uint64_t *peer_min;
+    int npeers;
+    uint32_t *active_mask;
+    double threshold;
+    uint64_t *list_count;
+    int64_t *list_idx;
+    double *list_val;
+    int64_t list_cap;
+} bez_reduce_opts;
+int bez_pair_sepsq_elev_ex(const bez_plan *plan, const double *d_cpts, int B, int N,
+                           int64_t pair_begin, int64_t npairs, double maxSep2,
+                           double *d_out, const bez_reduce_opts *opts, void *stream);
+int bez_speed_sq_elev_ex(const bez_plan *plan, const double *d_cpts, const double *d_tf,
+                         int B, int N, int veh_begin, int nveh, double alpha, double beta,
+                         double *d_out, const bez_reduce_opts *opts, void *stream);
 
 /* ---- A5: _maxSpeedConstraints / _minSpeedConstraints (optimization.py:349-422)
  * = Bezier.diff (bezier.py:497-519, same degree) -> normSquare ->

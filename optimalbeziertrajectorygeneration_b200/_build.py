@@ -26,6 +26,12 @@ UNITS = [
     ("plan.cu", []),
     ("constraints.cu", []),
     ("constraints_mma.cu", []),
+    ("constraints_mma_pair_a.cu", []),
+    ("constraints_mma_pair_b.cu", []),
+    ("constraints_mma_pair_c.cu", []),
+    ("constraints_mma_pair_d.cu", []),
+    ("constraints_mma_speed_a.cu", []),
+    ("constraints_mma_speed_b.cu", []),
     ("jacobian.cu", []),
     ("angrate.cu", []),
     ("curveops.cu", []),

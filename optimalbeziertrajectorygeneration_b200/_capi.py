@@ -30,6 +30,14 @@ _lib = _load()
 
 I, D, P, L64 = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64
 
+class ReduceOpts(ctypes.Structure):
+    """bez_reduce_opts of include/bezgpu.h."""
+    _fields_ = [("itemmin", ctypes.c_void_p), ("min_pitch", ctypes.c_int64), ("peer_min", ctypes.c_void_p),
+                ("npeers", ctypes.c_int), ("active_mask", ctypes.c_void_p), ("threshold", ctypes.c_double),
+                ("list_count", ctypes.c_void_p), ("list_idx", ctypes.c_void_p), ("list_val", ctypes.c_void_p),
+                ("list_cap", ctypes.c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/bezgpu.h declares
 SIGNATURES = {
     "bez_last_error": (ctypes.c_char_p, []),
@@ -45,6 +53,8 @@ SIGNATURES = {
     "bez_pair_sepsq_elev": (I, [c_plan_p, P, I, I, L64, L64, D, P, P, P]),
     "bez_pair_sepsq_elev_p2p": (I, [c_plan_p, P, I, I, L64, L64, D, P, P, P, I, P]),
     "bez_speed_sq_elev": (I, [c_plan_p, P, P, I, I, I, I, D, D, P, P]),
+    "bez_pair_sepsq_elev_ex": (I, [c_plan_p, P, I, I, L64, L64, D, P, ctypes.POINTER(ReduceOpts), P]),
+    "bez_speed_sq_elev_ex": (I, [c_plan_p, P, P, I, I, I, I, D, D, P, ctypes.POINTER(ReduceOpts), P]),
     "bez_angrate_tables_create": (I, [I, I, I, P, P, P, P, ctypes.POINTER(c_plan_p)]),
     "bez_angrate_tables_destroy": (I, [c_plan_p]),
     "bez_angrate_sq": (I, [c_plan_p, P, P, I, I, I, I, I, D, D, P, P]),

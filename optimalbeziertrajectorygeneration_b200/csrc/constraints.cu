@@ -70,7 +70,10 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
             // lanes past the end recompute the last item so every staged row is finite
             const long long gi = g0 + (lane < cnt ? lane : cnt - 1);
             const int b = (int)(gi / A.nitems);
-            stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, gi - (long long)b * A.nitems, 0, s);
+            const long long it = A.item_begin + gi - (long long)b * A.nitems;
+            int vi = (int)it, vj = 0;
+            if (MODE == PAIR) bez_pair_decode(it, A.N, vi, vj);
+            stage1_coeffs<N_, DIM, MODE>(A, PW, DW, b, vi, vj, s);
             double2 *row = rows + (size_t)lane * RS;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
@@ -96,10 +99,10 @@ sq_elev_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N
             double m0 = mb[0], m1 = mb[1], m2 = mb[2], m3 = mb[3];
 #pragma unroll
             for (int q = 4; q < 16; q += 4) {
-                m0 = dmin(m0, mb[q]); m1 = dmin(m1, mb[q + 1]);
-                m2 = dmin(m2, mb[q + 2]); m3 = dmin(m3, mb[q + 3]);
+                m0 = dmin_nan(m0, mb[q]); m1 = dmin_nan(m1, mb[q + 1]);
+                m2 = dmin_nan(m2, mb[q + 2]); m3 = dmin_nan(m3, mb[q + 3]);
             }
-            if (lane < cnt) A.itemmin[g0 + lane] = dmin(dmin(m0, m1), dmin(m2, m3));
+            if (lane < cnt) A.sinks.itemmin[g0 + lane] = dmin_nan(dmin_nan(m0, m1), dmin_nan(m2, m3));
         }
         __syncwarp();
     }
@@ -194,7 +197,7 @@ int launch_sq_elev(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     const bool two = A.LhPad > 32;      // more than one 32-column group: 2 column pairs per lane
     // the fused per-item minimum parks partial results in consumed rows, which
     // needs a single sweep over the columns (L <= 128) and rows of >= 16 doubles
-    const bool fused_min = A.itemmin && A.LhPad <= 64 && 2 * RowGeom<N_>::RS >= 16;
+    const bool fused_min = A.sinks.itemmin && A.LhPad <= 64 && 2 * RowGeom<N_>::RS >= 16;
     if (fused_min) {
         if constexpr (2 * RowGeom<N_>::RS >= 16)
             return two ? launch_sq_elev2<N_, DIM, MODE, 2, true>(plan, A, st)
@@ -202,9 +205,9 @@ int launch_sq_elev(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     }
     int rc = two ? launch_sq_elev2<N_, DIM, MODE, 2, false>(plan, A, st)
                  : launch_sq_elev2<N_, DIM, MODE, 1, false>(plan, A, st);
-    if (rc != BEZ_OK || !A.itemmin) return rc;
+    if (rc != BEZ_OK || !A.sinks.itemmin) return rc;
     const long long rows = (long long)A.B * A.nitems;         // rare shapes: separate reduction pass
-    item_min_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(A.out, rows, A.L, A.itemmin);
+    item_min_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(A.out, rows, A.L, A.sinks.itemmin);
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;
 }
@@ -237,10 +240,83 @@ int dispatch_degree(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) 
 
 }  // namespace
 
-extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, int B, int N,
-                                   int64_t pair_begin, int64_t npairs, double maxSep2,
-                                   double *d_out, double *d_pairmin, void *stream) {
-    BEZ_REQUIRE(plan && d_cpts && d_out, "NULL argument");
+// Packed active bitmask / compacted list from a [B][pitch] matrix of per-item minima: the
+// post-pass of the shapes whose kernels do not fuse it (the tensor-path kernels do, emit_minima).
+__global__ void emit_from_minima_kernel(bezmma::MinSinks S, long long total) {
+    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll;
+    const int lane = threadIdx.x & 31;
+    if (g0 >= total) return;
+    const long long f = g0 + lane;
+    const bool valid = f < total;
+    long long src = f;
+    if (S.min_pitch > 0 && valid) {
+        const long long b = f / S.nitems;
+        src = b * S.min_pitch + (f - b * S.nitems);
+    }
+    const double v = valid ? S.itemmin[src] : 0.0;
+    const bool act = valid && v < S.threshold;
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (S.mask && lane == 0) S.mask[g0 >> 5] = bal;
+    if (S.list_count && bal) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(S.list_count, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const long long pos = (long long)base + __popc(bal & ((1u << lane) - 1u));
+        if (act && pos < S.list_cap) { S.list_idx[pos] = f; S.list_val[pos] = v; }
+    }
+}
+
+static int fill_sinks(bezmma::MinSinks &S, const bez_reduce_opts *o, long long nitems, double *legacy_min) {
+    memset(&S, 0, sizeof(S));
+    S.nitems = nitems;
+    S.itemmin = legacy_min;
+    if (!o) return BEZ_OK;
+    if (o->itemmin) S.itemmin = o->itemmin;
+    BEZ_REQUIRE(o->min_pitch == 0 || o->min_pitch >= nitems, "min_pitch is smaller than the item count");
+    S.min_pitch = (o->min_pitch == nitems) ? 0 : o->min_pitch;
+    BEZ_REQUIRE(o->npeers >= 0 && o->npeers <= BEZ_MAX_PEERS && (o->npeers == 0 || o->peer_min), "bad peer list");
+    S.npeers = o->npeers;
+    for (int q = 0; q < o->npeers; ++q) S.peer_min[q] = reinterpret_cast<double *>((uintptr_t)o->peer_min[q]);
+    S.mask = o->active_mask;
+    S.threshold = o->threshold;
+    BEZ_REQUIRE(!o->list_count || (o->list_idx && o->list_val && o->list_cap >= 0), "incomplete active list");
+    S.list_count = (unsigned long long *)o->list_count;
+    S.list_idx = (long long *)o->list_idx;
+    S.list_val = o->list_val;
+    S.list_cap = o->list_cap;
+    return BEZ_OK;
+}
+
+// common tail of the pair / speed entry points
+static int run_sq_elev(const bez_plan *plan, SqElevArgs &A, int mode, const bez_reduce_opts *opts,
+                       double *legacy_min, cudaStream_t st) {
+    if (int rc = fill_sinks(A.sinks, opts, A.nitems, legacy_min)) return rc;
+    const bezmma::MinSinks &S = A.sinks;
+    const bool derived = S.mask || S.list_count;
+    BEZ_REQUIRE(A.out || S.itemmin || derived || S.npeers > 0, "nothing to compute: no rows and no minima requested");
+    A.flags = bez_sq_elev_mma_flags();
+    if (bez_sq_elev_mma_supported(plan) && (A.out || mode == PAIR))
+        return bez_sq_elev_mma(plan, A, mode, st);
+    // column-stationary DFMA kernels: rows are always written; minima to the local matrix only
+    if (!A.out || S.npeers > 0) {
+        bez_set_error("degree %d / elevation %d / dim %d is outside the tensor-path kernels: rows cannot be "
+                      "skipped and the fused peer stores are not available", plan->n, plan->elev, plan->dim);
+        return BEZ_EUNSUPPORTED;
+    }
+    BEZ_REQUIRE(!derived || S.itemmin, "the active mask / list of this shape needs the itemmin matrix");
+    BEZ_REQUIRE(S.min_pitch == 0, "this shape needs min_pitch == nitems");
+    int rc = mode == PAIR ? dispatch_degree<PAIR>(plan, A, st) : dispatch_degree<SPEED>(plan, A, st);
+    if (rc != BEZ_OK || !derived) return rc;
+    const long long total = A.nitems * (long long)A.B;
+    emit_from_minima_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, total);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
+
+extern "C" int bez_pair_sepsq_elev_ex(const bez_plan *plan, const double *d_cpts, int B, int N,
+                                      int64_t pair_begin, int64_t npairs, double maxSep2,
+                                      double *d_out, const bez_reduce_opts *opts, void *stream) {
+    BEZ_REQUIRE(plan && d_cpts, "NULL argument");
     BEZ_REQUIRE(B >= 0 && N >= 0, "negative size");
     const long long P = (long long)N * (N - 1) / 2;
     BEZ_REQUIRE(pair_begin >= 0 && npairs >= 0 && pair_begin + npairs <= (P > 0 ? P : 0),
@@ -248,56 +324,56 @@ extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, i
     if (B == 0 || npairs == 0) return BEZ_OK;
     BEZ_ON_DEVICE(plan->device);
     SqElevArgs A;
-    A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = d_pairmin;
+    A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out;
     A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
-    A.alpha = 1.0; A.beta = -maxSep2; A.npeers = 0;
-    if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, PAIR, (cudaStream_t)stream);
-    return dispatch_degree<PAIR>(plan, A, (cudaStream_t)stream);
+    A.alpha = 1.0; A.beta = -maxSep2;
+    return run_sq_elev(plan, A, PAIR, opts, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int bez_pair_sepsq_elev(const bez_plan *plan, const double *d_cpts, int B, int N,
+                                   int64_t pair_begin, int64_t npairs, double maxSep2,
+                                   double *d_out, double *d_pairmin, void *stream) {
+    BEZ_REQUIRE(d_out, "NULL argument");
+    bez_reduce_opts o;
+    memset(&o, 0, sizeof(o));
+    o.itemmin = d_pairmin;
+    return bez_pair_sepsq_elev_ex(plan, d_cpts, B, N, pair_begin, npairs, maxSep2, d_out, &o, stream);
 }
 
 extern "C" int bez_pair_sepsq_elev_p2p(const bez_plan *plan, const double *d_cpts, int B, int N,
                                        int64_t pair_begin, int64_t npairs, double maxSep2,
                                        double *d_out, double *d_pairmin,
                                        const uint64_t *h_peer_min, int npeers, void *stream) {
-    BEZ_REQUIRE(plan && d_cpts && d_out && d_pairmin, "NULL argument");
-    BEZ_REQUIRE(B >= 0 && N >= 0, "negative size");
-    BEZ_REQUIRE(npeers >= 0 && npeers <= BEZ_MAX_PEERS && (npeers == 0 || h_peer_min), "bad peer list");
-    const long long P = (long long)N * (N - 1) / 2;
-    BEZ_REQUIRE(pair_begin >= 0 && npairs >= 0 && pair_begin + npairs <= (P > 0 ? P : 0),
-                "pair range outside the N(N-1)/2 list");
-    if (!bez_sq_elev_mma_supported(plan)) {
-        bez_set_error("bez_pair_sepsq_elev_p2p: degree %d / elevation %d is outside the tensor-path kernels",
-                      plan->n, plan->elev);
-        return BEZ_EUNSUPPORTED;
-    }
-    if (B == 0 || npairs == 0) return BEZ_OK;
-    BEZ_ON_DEVICE(plan->device);
-    SqElevArgs A;
-    A.cpts = d_cpts; A.tf = nullptr; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = d_pairmin;
-    A.item_begin = pair_begin; A.nitems = npairs; A.B = B; A.N = N;
-    A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
-    A.alpha = 1.0; A.beta = -maxSep2; A.npeers = npeers;
-    for (int q = 0; q < BEZ_MAX_PEERS; ++q)
-        A.peer_min[q] = q < npeers ? reinterpret_cast<double *>((uintptr_t)h_peer_min[q]) : nullptr;
-    return bez_sq_elev_mma(plan, A, PAIR, (cudaStream_t)stream);
+    BEZ_REQUIRE(d_out && d_pairmin, "NULL argument");
+    bez_reduce_opts o;
+    memset(&o, 0, sizeof(o));
+    o.itemmin = d_pairmin;
+    o.peer_min = h_peer_min;
+    o.npeers = npeers;
+    return bez_pair_sepsq_elev_ex(plan, d_cpts, B, N, pair_begin, npairs, maxSep2, d_out, &o, stream);
 }
 
-extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, const double *d_tf,
-                                 int B, int N, int veh_begin, int nveh,
-                                 double alpha, double beta, double *d_out, void *stream) {
+extern "C" int bez_speed_sq_elev_ex(const bez_plan *plan, const double *d_cpts, const double *d_tf,
+                                    int B, int N, int veh_begin, int nveh, double alpha, double beta,
+                                    double *d_out, const bez_reduce_opts *opts, void *stream) {
     BEZ_REQUIRE(plan && d_cpts && d_tf && d_out, "NULL argument");
     BEZ_REQUIRE(B >= 0 && N >= 0 && veh_begin >= 0 && nveh >= 0 && veh_begin + nveh <= N,
                 "vehicle range outside [0, N)");
     if (B == 0 || nveh == 0) return BEZ_OK;
     BEZ_ON_DEVICE(plan->device);
     SqElevArgs A;
-    A.cpts = d_cpts; A.tf = d_tf; A.PQ = plan->d_PQ; A.out = d_out; A.itemmin = nullptr;
+    A.cpts = d_cpts; A.tf = d_tf; A.PQ = plan->d_PQ; A.out = d_out;
     A.item_begin = veh_begin; A.nitems = nveh; A.B = B; A.N = N;
     A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
-    A.alpha = alpha; A.beta = beta; A.npeers = 0;
-    if (bez_sq_elev_mma_supported(plan)) return bez_sq_elev_mma(plan, A, SPEED, (cudaStream_t)stream);
-    return dispatch_degree<SPEED>(plan, A, (cudaStream_t)stream);
+    A.alpha = alpha; A.beta = beta;
+    return run_sq_elev(plan, A, SPEED, opts, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int bez_speed_sq_elev(const bez_plan *plan, const double *d_cpts, const double *d_tf,
+                                 int B, int N, int veh_begin, int nveh,
+                                 double alpha, double beta, double *d_out, void *stream) {
+    return bez_speed_sq_elev_ex(plan, d_cpts, d_tf, B, N, veh_begin, nveh, alpha, beta, d_out, nullptr, stream);
 }
 
 extern "C" int bez_assemble_cpts(const bez_plan *plan, const double *d_x, int B, int nvar,

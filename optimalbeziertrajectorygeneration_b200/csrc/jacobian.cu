@@ -231,9 +231,10 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
     double *obuf = rows + kRowsDoubles;
     for (int i = lane; i < kRowsDoubles; i += 32) rows[i] = 0.0;     // padding slots must be 0
     const unsigned obuf_s = (unsigned)__cvta_generic_to_shared(obuf);
-    const LaneGeom G = lane_geom(lane, A.Lh);
-    BFrags<N_> Bf;
-    load_bfrags<N_>(Bf, A.PQ, A.Lh, A.LhPad, lane);
+    BFrags<N_, 4> Bf;
+    load_bfrags<N_, 4>(Bf, A.PQ, A.L, A.LhPad, lane);
+    MinSinks no_sinks;
+    memset(&no_sinks, 0, sizeof(no_sinks));
     __syncwarp();
     const long long nwt = (A.nitems + 31) >> 5;
     const long long gwarp = (long long)blockIdx.x * kWarps + warp;
@@ -256,7 +257,8 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
             row[slot_e(N_)] = s[N_] * A.scale;
         }
         __syncwarp();
-        mma_tile<N_, 0>(rows, obuf, obuf_s, Bf, G, A.out + (size_t)t0 * A.L, nullptr, cnt, A.L, A.Lh, 0.0, lane, base_aligned);
+        mma_tile<N_, 4, 0, true>(rows, obuf, obuf_s, Bf, A.out + (size_t)t0 * A.L, no_sinks, t0, cnt, A.L, 0.0, lane,
+                                 base_aligned);
         __syncwarp();
     }
     if (lane == 0) bulk_wait_all();

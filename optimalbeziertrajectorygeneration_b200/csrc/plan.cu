@@ -47,7 +47,12 @@ int bez_kernel_config(const void *func, int threads, size_t shmem, int *sms, int
             return BEZ_OK;
         }
     KernelConfig c{func, dev, threads, shmem, 148, 1};
-    if (shmem > 48 * 1024)
+    // the opt-in only ever grows: a smaller request must not lower what an earlier (cached)
+    // configuration of the same kernel on this device relies on
+    size_t granted = 48 * 1024;
+    for (const KernelConfig &o : g_cfg)
+        if (o.func == func && o.device == dev && o.shmem > granted) granted = o.shmem;
+    if (shmem > granted)
         BEZ_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     BEZ_CUDA(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
     BEZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, func, threads, shmem));

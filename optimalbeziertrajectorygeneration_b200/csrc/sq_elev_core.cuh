@@ -24,6 +24,10 @@ __host__ __device__ constexpr int widx(int i, int j) {   // i <= j
 
 // min without fmin()'s NaN bookkeeping (1 DSETP + 2 SEL instead of ~6 instructions)
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+// NaN-propagating variant for reductions that mix real values with +inf placeholders (idle
+// lanes, dead columns): a NaN row must yield a NaN minimum, like numpy's min (a row is NaN
+// in all its values or in none, because every output sums all 2n+1 coefficients).
+__device__ __forceinline__ double dmin_nan(double a, double b) { return (a < b || a != a) ? a : b; }
 
 // Min over the L outputs of each item: separate pass for the shapes the fused
 // epilogue does not cover (L > 128 or degree < 4).
@@ -34,9 +38,9 @@ static __global__ void item_min_kernel(const double *__restrict__ vals, long lon
     if (warp >= nrows) return;
     const double *r = vals + (size_t)warp * L;
     double m = INFINITY;
-    for (int i = lane; i < L; i += 32) m = dmin(m, r[i]);
+    for (int i = lane; i < L; i += 32) m = dmin_nan(m, r[i]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = dmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int o = 16; o > 0; o >>= 1) m = dmin_nan(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) mins[warp] = m;
 }
 
@@ -150,10 +154,10 @@ __device__ __forceinline__ void sweep_columns(double2 *rows, const double *tab, 
                 double mn = live[0] ? se[u][0] - fabs(so[u][0]) : INFINITY;
 #pragma unroll
                 for (int c = 1; c < CPL; ++c)
-                    mn = live[c] ? dmin(mn, se[u][c] - fabs(so[u][c])) : mn;
+                    mn = live[c] ? dmin_nan(mn, se[u][c] - fabs(so[u][c])) : mn;
                 // fold the warp in half, then park the 16 partial minima in the
                 // (already consumed) staged row of this item
-                mn = dmin(mn, __shfl_xor_sync(0xffffffffu, mn, 16));
+                mn = dmin_nan(mn, __shfl_xor_sync(0xffffffffu, mn, 16));
                 if (lane < 16) reinterpret_cast<double *>(rows + (size_t)(p0 + u) * RS)[lane] = mn;
             }
         }

@@ -66,64 +66,105 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Folded elevation weights in B-fragment order, register resident for the whole kernel.
-template <int N_> struct BFrags {
-    double p[8][Geom<N_>::KE];
-    double q[8][Geom<N_>::KO > 0 ? Geom<N_>::KO : 1];
+// NP = n-tile pairs of the shape: 16 NP column-pair slots cover Lh <= 16 NP, i.e. L <= 32 NP
+// (NP = 4: the headline shapes 65 <= L <= 128; NP = 2: 33..64; NP = 1: L <= 32).
+template <int N_, int NP> struct BFrags {
+    double p[2 * NP][Geom<N_>::KE];
+    double q[2 * NP][Geom<N_>::KO > 0 ? Geom<N_>::KO : 1];
 };
 
-template <int N_>
-__device__ __forceinline__ void load_bfrags(BFrags<N_> &B, const double *__restrict__ PQ, int Lh, int LhPad,
+template <int N_, int NP>
+__device__ __forceinline__ void load_bfrags(BFrags<N_, NP> &B, const double *__restrict__ PQ, int L, int LhPad,
                                             int lane) {
     constexpr int NC = N_ + 1;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int ni = 0; ni < 8; ++ni) {
-        const int col = col_of(ni, g);
-        const bool live = col < LhPad;          // columns >= Lh hold mirrored weights (plan.cu): valid duplicates
+    for (int ni = 0; ni < 2 * NP; ++ni) {
+        // Slots Lh <= c <= M hold mirrored weights (plan.cu): valid duplicates.  Slots beyond the
+        // row (c > M, only possible for L < 16 NP, i.e. NP = 1 and L < 16) take the weights of
+        // column pair 0: their values are valid duplicates for the minimum, their stores are
+        // predicated off in the epilogue.
+        int col = col_of(ni, g);
+        if (col > L - 1) col = 0;
 #pragma unroll
         for (int ks = 0; ks < Geom<N_>::KE; ++ks) {
             const int j = 4 * ks + t;
-            B.p[ni][ks] = (live && j <= N_) ? __ldg(PQ + (size_t)j * LhPad + col) : 0.0;
+            B.p[ni][ks] = (j <= N_) ? __ldg(PQ + (size_t)j * LhPad + col) : 0.0;
         }
 #pragma unroll
         for (int ks = 0; ks < Geom<N_>::KO; ++ks) {
             const int j = 4 * ks + t;
-            B.q[ni][ks] = (live && j < N_) ? __ldg(PQ + (size_t)(NC + j) * LhPad + col) : 0.0;
+            B.q[ni][ks] = (j < N_) ? __ldg(PQ + (size_t)(NC + j) * LhPad + col) : 0.0;
         }
     }
 }
 
-// Per-lane constants of the epilogue.
-struct LaneGeom {
-    int g, t;
+// Where the per-item minima of a launch go (all optional).  f = flattened item index
+// b * nitems + item of the launch.
+struct MinSinks {
+    double *itemmin;                    // [B][pitch] (pitch = nitems unless min_pitch > 0)
+    long long min_pitch, nitems;
+    double *peer_min[BEZ_MAX_PEERS];    // fused all-gather: the same matrix on other GPUs (NVLink)
+    int npeers;
+    unsigned *mask;                     // bit f of word f >> 5 = (min < threshold)
+    double threshold;
+    unsigned long long *list_count;     // compacted (f, min) list of the items with min < threshold,
+    long long *list_idx;                //   warp-aggregated atomic append (order unspecified);
+    double *list_val;                   //   entries past list_cap are dropped but still counted
+    long long list_cap;
 };
-__device__ __forceinline__ LaneGeom lane_geom(int lane, int /*Lh*/) {
-    LaneGeom G;
-    G.g = lane >> 2;
-    G.t = lane & 3;
-    return G;
+
+// v = minimum of item (8 t + g) held by lane (g, t) = 4 g + t  ->  all sinks.  g0 = flattened
+// index of the tile's first item (a multiple of 32), cnt = live items of the tile.
+__device__ __forceinline__ void emit_minima(const MinSinks &S, double v, long long g0, int cnt, int lane) {
+    // to item order: lane l takes the minimum of item l (coalesced stores, ballot bit = item)
+    const double vi = __shfl_sync(0xffffffffu, v, 4 * (lane & 7) + (lane >> 3));
+    const bool valid = lane < cnt;
+    const long long f = g0 + lane;
+    long long dst = f;
+    if (S.min_pitch > 0) {                              // rows of the destination are wider than this launch
+        const long long b = f / S.nitems;
+        dst = b * S.min_pitch + (f - b * S.nitems);
+    }
+    if (valid) {
+        if (S.itemmin) S.itemmin[dst] = vi;
+#pragma unroll
+        for (int q = 0; q < BEZ_MAX_PEERS; ++q)
+            if (q < S.npeers) S.peer_min[q][dst] = vi;
+    }
+    if (S.mask || S.list_count) {                       // warp-uniform
+        const bool act = valid && vi < S.threshold;
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        if (S.mask && lane == 0) S.mask[g0 >> 5] = bal;
+        if (S.list_count && bal) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(S.list_count, (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const long long pos = (long long)base + __popc(bal & ((1u << lane) - 1u));
+            if (act && pos < S.list_cap) { S.list_idx[pos] = f; S.list_val[pos] = vi; }
+        }
+    }
 }
 
 // One warp tile: rows = staged (e,o) rows of 32 items, obuf = 2 x [8][L] doubles of
 // staging, obuf_s = its shared-window address,
-// outg = global address of the tile's first output row (rows contiguous, pitch L),
-// ming = per-item minimum (MINMODE != 0).  base_aligned: the output base address is a
-// multiple of 16 bytes (then every full m-tile block is, too).  m-tile mi uses staging
-// buffer mi & 1 (at most one bulk read is left pending).
+// outg = global address of the tile's first output row (rows contiguous, pitch L).
+// base_aligned: the output base address is a multiple of 16 bytes (then every full m-tile
+// block is, too).  m-tile mi uses staging buffer mi & 1 (at most one bulk read is left pending).
+// MINMODE: per-item minimum -> emit_minima;  STORE = false: the rows are not written at all
+// (callers that only want the minima, e.g. the sequential-planning constraint).
 //
-// Schedule of one m-tile (8 items): the n-tiles are processed in pairs; the 12 DMMAs of
+// Schedule of one m-tile (8 items): the n-tiles are processed in pairs; the DMMAs of
 // pair p+1 (4 independent accumulator chains, round-robin over the k-steps) are issued
 // before the epilogue of pair p, so the fp64 pipe always has independent work queued
-// behind the DADD/STS of the epilogue (in-order issue: without this the epilogue waits
-// out the full DMMA latency, 38 % "wait" stalls in profiles/r01_ncu_pair_kernel_mma_v1).
-template <int N_, int MINMODE>
+// behind the DADD/STS of the epilogue.
+template <int N_, int NP, int MINMODE, bool STORE>
 __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
-                                         const BFrags<N_> &B, const LaneGeom &G,
-                                         double *__restrict__ outg, double *__restrict__ ming, int cnt,
-                                         int L, int Lh, double beta, int lane, bool base_aligned,
-                                         double *const *peer_min = nullptr, int npeers = 0, long long peer_off = 0) {
+                                         const BFrags<N_, NP> &B, double *__restrict__ outg,
+                                         const MinSinks &S, long long g0, int cnt,
+                                         int L, double beta, int lane, bool base_aligned, int dbg = 0) {
     constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO;
-    const int g = G.g, t = G.t;
+    const int g = lane >> 2, t = lane & 3;
     const int M = L - 1;
     double mnv[4];
 #pragma unroll
@@ -145,7 +186,7 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         double *ob = obuf + (size_t)par * 8 * L;
         double *of = ob + g * L + 4 * t;           // forward cursor of this lane (column 4 t of row g)
         double *om = ob + g * L + M - 4 * t;       // mirror cursor
-        double mnp[4];                              // one minimum per n-tile pair: short dependency chains
+        double mnp[NP];                             // one minimum per n-tile pair: short dependency chains
         double C[2][2][4];
         auto mma_pair = [&](int p, double (&c)[2][4]) {
 #pragma unroll
@@ -165,11 +206,18 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int cb = 16 * p + 2 * u;              // first column of n-tile 2 p + u
-                const double f0 = c[u][0] + c[u][2], m0 = c[u][0] - c[u][2];
-                const double f1 = c[u][1] + c[u][3], m1 = c[u][1] - c[u][3];
-                // every column slot is a valid output pair (slots >= Lh duplicate their mirror
-                // slot bit for bit, see plan.cu), so there is no liveness test on this path
-                of[cb] = f0; om[-cb] = m0; of[cb + 1] = f1; om[-cb - 1] = m1;
+                if (STORE) {
+                    const double f0 = c[u][0] + c[u][2], m0 = c[u][0] - c[u][2];
+                    const double f1 = c[u][1] + c[u][3], m1 = c[u][1] - c[u][3];
+                    if (NP > 1) {
+                        // every column slot is a valid output pair (slots >= Lh duplicate their
+                        // mirror slot bit for bit, see plan.cu): no liveness test on this path
+                        of[cb] = f0; om[-cb] = m0; of[cb + 1] = f1; om[-cb - 1] = m1;
+                    } else {                                // L < 16 is possible: slots beyond the row
+                        if (cb + 4 * t <= M) { of[cb] = f0; om[-cb] = m0; }
+                        if (cb + 4 * t + 1 <= M) { of[cb + 1] = f1; om[-cb - 1] = m1; }
+                    }
+                }
                 if (MINMODE) {                              // min(se+so, se-so) = se - |so|, one DADD
                     cand[u][0] = c[u][0] - fabs(c[u][2]);
                     cand[u][1] = c[u][1] - fabs(c[u][3]);
@@ -179,12 +227,14 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         };
 
         mma_pair(0, C[0]);
-        // the bulk read of this staging buffer (issued two m-tiles ago) must be done
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
+        if (STORE) {
+            // the bulk read of this staging buffer (issued two m-tiles ago) must be done
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+        }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            if (p < 3) mma_pair(p + 1, C[(p + 1) & 1]);
+        for (int p = 0; p < NP; ++p) {
+            if (p < NP - 1) mma_pair(p + 1, C[(p + 1) & 1]);
             else if (mi < 3) {                              // A fragments of the next m-tile
                 const double *an = ar + (size_t)8 * (mi + 1) * kRowStride;
 #pragma unroll
@@ -194,20 +244,30 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
             }
             epilogue(p, C[p & 1]);
         }
-        if (MINMODE) mnv[mi] = dmin(dmin(mnp[0], mnp[1]), dmin(mnp[2], mnp[3]));
-        fence_async_smem();                         // generic-proxy writes -> visible to the TMA read
-        __syncwarp();
-        const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
-        double *dst = outg + (size_t)8 * mi * L;
-        const unsigned bytes = (unsigned)(nrows * L) * 8u;
-        if (base_aligned && (nrows == 8 || (bytes & 15u) == 0)) {
-            if (lane == 0) { bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes); bulk_commit(); }
-        } else {                                    // odd row count x odd L or unaligned base
-            for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
-            if (lane == 0) bulk_commit();           // empty group keeps the count in step
+        if (MINMODE) {
+            double m = mnp[0];
+#pragma unroll
+            for (int p = 1; p < NP; ++p) m = dmin(m, mnp[p]);
+            mnv[mi] = m;
+        }
+        if (STORE) {
+            if (!(dbg & 8)) fence_async_smem();     // generic-proxy writes -> visible to the TMA read
+            __syncwarp();
+            const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
+            double *dst = outg + (size_t)8 * mi * L;
+            const unsigned bytes = (unsigned)(nrows * L) * 8u;
+            if (base_aligned && (nrows == 8 || (bytes & 15u) == 0)) {
+                if (lane == 0) {
+                    if (!(dbg & 4)) bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes);
+                    bulk_commit();
+                }
+            } else {                                // odd row count x odd L or unaligned base
+                for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
+                if (lane == 0) bulk_commit();       // empty group keeps the count in step
+            }
         }
     }
-    if (cnt <= 24) {                                // short tile: realign the buffer rotation
+    if (STORE && cnt <= 24) {                       // short tile: realign the buffer rotation
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
     }
@@ -222,14 +282,7 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         const double a1 = dmin(b0 ? mnv[3] : mnv[2], r1);      // m-tile (t & 1) + 2
         const double r2 = __shfl_xor_sync(0xffffffffu, b1 ? a0 : a1, 2);
         const double v = dmin(b1 ? a1 : a0, r2);               // m-tile t
-        if (8 * t + g < cnt) {
-            ming[8 * t + g] = v;
-            if (npeers > 0) {                               // fused all-gather: NVLink peer stores
-#pragma unroll
-                for (int q = 0; q < BEZ_MAX_PEERS; ++q)
-                    if (q < npeers) peer_min[q][peer_off + 8 * t + g] = v;
-            }
-        }
+        emit_minima(S, v, g0, cnt, lane);
     }
 }
 

@@ -138,6 +138,52 @@ def _on_device(method):
     return wrapper
 
 
+class ActiveSet:
+    """Device destination of the reduced result of a fused kernel launch over ``nitems_total``
+    flattened items (f = b * nitems + item): the packed bitmask ``mask`` (bit f & 31 of word
+    f >> 5 = min < threshold) and, with ``capacity`` > 0, the compacted list ``idx[k]`` = f,
+    ``val[k]`` = min of the active items (``count`` = how many there are; order unspecified;
+    ``count`` > ``capacity`` means the list overflowed and only the mask is complete).
+    All three live in ONE device buffer so that a single D2H copy brings the whole result:
+    [count (8 B) | mask words | idx | val]."""
+
+    def __init__(self, nitems_total, capacity, device, threshold=0.0):
+        self.nitems_total = int(nitems_total)
+        self.capacity = int(capacity)
+        self.threshold = float(threshold)
+        self.words = (self.nitems_total + 31) // 32
+        self.mask_slots = (self.words + 1) // 2                 # 8-byte slots holding the mask
+        self.nslots = 1 + self.mask_slots + 2 * self.capacity
+        self.buf = torch.zeros(self.nslots, dtype=torch.int64, device=device)
+        self.count = self.buf[0:1]
+        self.mask = self.buf[1:1 + self.mask_slots].view(torch.int32)
+        self.idx = self.buf[1 + self.mask_slots:1 + self.mask_slots + self.capacity]
+        self.val = self.buf[1 + self.mask_slots + self.capacity:].view(F64)
+
+    def check(self, nitems_total, device):
+        if int(nitems_total) != self.nitems_total or self.buf.device != device:
+            raise ValueError("ActiveSet was sized for %d items on %s" % (self.nitems_total, self.buf.device))
+
+    def reset(self):
+        """Zeroes the list counter (stream ordered; the mask is overwritten by the kernel)."""
+        self.count.zero_()
+
+    @staticmethod
+    def decode(host_buf, nitems_total, capacity):
+        """host copy of ``buf`` (int64 numpy array) -> (flags bool [nitems_total], idx, val,
+        overflow): idx / val sorted by idx."""
+        words = (nitems_total + 31) // 32
+        slots = (words + 1) // 2
+        count = int(host_buf[0])
+        mask = host_buf[1:1 + slots].view(np.uint32)[:words]
+        flags = np.unpackbits(mask.view(np.uint8), bitorder='little')[:nitems_total].astype(bool)
+        k = min(count, capacity)
+        idx = host_buf[1 + slots:1 + slots + k]
+        val = host_buf[1 + slots + capacity:1 + slots + capacity + k].view(np.float64)
+        order = np.argsort(idx, kind='stable')
+        return flags, idx[order], val[order], count > capacity
+
+
 class ConstraintEngine:
     """Everything a BezOptimization model needs on the device.
 
@@ -206,6 +252,13 @@ class ConstraintEngine:
             self._pinned[key] = buf
         return buf[:numel]
 
+    def _pinned_buf_i64(self, key, numel):
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(max(numel, 1), dtype=torch.int64, pin_memory=True)
+            self._pinned[key] = buf
+        return buf[:numel]
+
     @_on_device
     def upload(self, X):
         """host float64 [B, nvar] -> device tensor, through pinned memory."""
@@ -269,13 +322,40 @@ class ConstraintEngine:
         return cpts, tf
 
     # -- A1-A4 --------------------------------------------------------------
+    def _reduce_opts(self, B, nitems, itemmin, min_pitch, peer_ptrs, active):
+        """ctypes bez_reduce_opts (+ the objects that must outlive the call)."""
+        o = _capi.ReduceOpts()
+        keep = []
+        if itemmin is not None:
+            o.itemmin = itemmin.data_ptr()
+        o.min_pitch = int(min_pitch or 0)
+        if peer_ptrs:
+            arr = (ctypes.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+            keep.append(arr)
+            o.peer_min = ctypes.addressof(arr)
+            o.npeers = len(peer_ptrs)
+        if active is not None:
+            active.check(B * nitems, self.device)
+            o.active_mask = active.mask.data_ptr()
+            o.threshold = float(active.threshold)
+            if active.capacity > 0:
+                o.list_count = active.count.data_ptr()
+                o.list_idx = active.idx.data_ptr()
+                o.list_val = active.val.data_ptr()
+                o.list_cap = int(active.capacity)
+        return o, keep
+
     @_on_device
     def separation(self, cpts, elev, max_sep, pair_begin=0, npairs=None, out=None, pairmin=None,
-                   n_curves=None, peer_ptrs=None):
+                   n_curves=None, peer_ptrs=None, rows=True, min_pitch=None, active=None):
         """Fused sub -> normSquare -> elev -> -maxSep^2 over a range of the
         lexicographic pair list.  Returns out [B, npairs, L] (device).
+        ``pairmin`` [B, npairs] (or, with ``min_pitch``, a view of a wider [B, min_pitch] matrix
+        starting at this range's first column): min over each pair's L values.
         ``peer_ptrs``: device addresses in other GPUs' gathered per-pair-minimum matrices
-        (sharding.PeerMinima); the kernel then also stores every minimum there over NVLink."""
+        (sharding.PeerMinima); the kernel then also stores every minimum there over NVLink.
+        ``active``: an :class:`ActiveSet` that receives the packed bitmask / compacted list of
+        the pairs with minimum < threshold.  ``rows=False``: no rows are written (returns None)."""
         plan = self.plan(elev)
         B = int(cpts.shape[0])
         N = int(cpts.shape[1]) if n_curves is None else int(n_curves)
@@ -284,29 +364,39 @@ class ConstraintEngine:
         if pair_begin < 0 or npairs < 0 or pair_begin + npairs > num_pairs(N):
             raise ValueError("pair range [%d, %d) outside the %d pairs" % (pair_begin, pair_begin + npairs, num_pairs(N)))
         self._check(cpts, (B, int(cpts.shape[1]), self.row_stride), "cpts")
-        if out is None:
-            out = torch.empty((B, npairs, plan.L), dtype=F64, device=self.device)
-        self._check(out, (B, npairs, plan.L), "out")
-        self._check(pairmin, (B, npairs), "pairmin")
-        if peer_ptrs:
-            if pairmin is None:
-                raise ValueError("peer_ptrs needs the local pairmin destination")
-            if pair_begin != 0 or npairs != num_pairs(N):
-                # the kernel addresses the peers' matrices with the same [B, npairs] pitch as the
-                # local one: a sub-range would land in the wrong rows
-                raise ValueError("peer_ptrs needs the full pair list (pair_begin = 0, npairs = P)")
-            arr = (ctypes.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
-            _capi.call("bez_pair_sepsq_elev_p2p", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
-                       float(max_sep) ** 2, _ptr(out), _ptr(pairmin), ctypes.addressof(arr), len(peer_ptrs),
-                       self._st())
-            return out
-        _capi.call("bez_pair_sepsq_elev", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
-                   float(max_sep) ** 2, _ptr(out), _ptr(pairmin), self._st())
+        if rows:
+            if out is None:
+                out = torch.empty((B, npairs, plan.L), dtype=F64, device=self.device)
+            self._check(out, (B, npairs, plan.L), "out")
+        else:
+            out = None
+            if pairmin is None and active is None and not peer_ptrs:
+                raise ValueError("rows=False needs pairmin, active or peer_ptrs")
+        if min_pitch:
+            if pairmin is None or int(min_pitch) < npairs:
+                raise ValueError("min_pitch needs pairmin and must be >= npairs")
+            if pairmin.dtype != F64 or pairmin.device != self.device or pairmin.stride(-1) != 1 or \
+                    (B > 1 and pairmin.stride(0) != int(min_pitch)) or pairmin.shape[0] != B or pairmin.shape[1] < npairs:
+                raise ValueError("pairmin must be a float64 view [B, >= npairs] with row pitch min_pitch")
+        else:
+            self._check(pairmin, (B, npairs), "pairmin")
+        if peer_ptrs and pairmin is None:
+            raise ValueError("peer_ptrs needs the local pairmin destination")
+        if peer_ptrs and not min_pitch and (pair_begin != 0 or npairs != num_pairs(N)):
+            # the kernel addresses the peers' matrices with the same pitch as the local one:
+            # a sub-range needs min_pitch (and pointers offset to the range's first column)
+            raise ValueError("peer_ptrs with a pair sub-range needs min_pitch")
+        opts, keep = self._reduce_opts(B, npairs, pairmin, min_pitch, peer_ptrs, active)
+        _capi.call("bez_pair_sepsq_elev_ex", plan.handle, _ptr(cpts), B, N, int(pair_begin), int(npairs),
+                   float(max_sep) ** 2, _ptr(out), ctypes.byref(opts), self._st())
+        del keep
         return out
 
     # -- A5 -------------------------------------------------------------------
     @_on_device
-    def speed(self, cpts, tf, elev, alpha, beta, veh_begin=0, nveh=None, out=None):
+    def speed(self, cpts, tf, elev, alpha, beta, veh_begin=0, nveh=None, out=None, vehmin=None, active=None):
+        """alpha * (squared speed control points) + beta, [B, nveh, L]; ``vehmin`` [B, nveh]
+        receives the minimum over each vehicle's L values, ``active`` its bitmask / list."""
         plan = self.plan(elev)
         B = int(cpts.shape[0])
         N = int(cpts.shape[1])
@@ -317,8 +407,13 @@ class ConstraintEngine:
         self._check(cpts, (B, N, self.row_stride), "cpts")
         self._check(tf, (B,), "tf")
         self._check(out, (B, nveh, plan.L), "out")
-        _capi.call("bez_speed_sq_elev", plan.handle, _ptr(cpts), _ptr(tf), B, N, int(veh_begin),
-                   int(nveh), float(alpha), float(beta), _ptr(out), self._st())
+        self._check(vehmin, (B, nveh), "vehmin")
+        if active is not None and vehmin is None:
+            vehmin = torch.empty((B, nveh), dtype=F64, device=self.device)
+        opts, keep = self._reduce_opts(B, nveh, vehmin, None, None, active)
+        _capi.call("bez_speed_sq_elev_ex", plan.handle, _ptr(cpts), _ptr(tf), B, N, int(veh_begin),
+                   int(nveh), float(alpha), float(beta), _ptr(out), ctypes.byref(opts), self._st())
+        del keep
         return out
 
     # -- A6 -------------------------------------------------------------------

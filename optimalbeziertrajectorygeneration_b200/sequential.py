@@ -6,10 +6,12 @@ every already planned trajectory i,
 (SequentialSwarm.py:62-67, R = 10), i.e. one scalar per frozen trajectory.  With the new
 vehicle as curve 0 the pairs (0, 1), (0, 2), ... are the *first* K pairs of the lexicographic
 pair list, so this is the fused pair kernel over the range [0, K) with its in-kernel per-pair
-minimum; the K x L elevated control points are produced in HBM on the way (scratch) and only
-the K minima are returned.  x-batches (the FD points of the new vehicle) go through the same
+minimum and no row stores (``d_out = NULL``): only the K minima are produced and returned.  x-batches (the FD points of the new vehicle) go through the same
 launch.
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 
@@ -55,10 +57,17 @@ class FrozenSwarm:
         head = np.zeros((B, self.S))
         head[:, :self.dim * (self.n + 1)] = Y.reshape(B, -1)
         cpts[:, 0] = torch.as_tensor(head, device=self.device)      # the new vehicle: curve 0
-        scratch = torch.empty((B, K, self.plan.L), dtype=F64, device=self.device)
         minima = torch.empty((B, K), dtype=F64, device=self.device)
-        _capi.call("bez_pair_sepsq_elev", self.plan.handle, _engine._ptr(cpts), B, N, 0, K,
-                   float(max_sep) ** 2, _engine._ptr(scratch), _engine._ptr(minima), _engine._stream())
+        opts = _capi.ReduceOpts()
+        opts.itemmin = minima.data_ptr()
+        # minima only: the tensor-path kernels skip the K x L rows altogether (reduced epilogue);
+        # shapes outside them (degree > 15, L > 128, dim 1) need the rows as scratch
+        scratch = None
+        if not (self.n <= 15 and self.plan.L <= 128 and self.dim >= 2) or os.environ.get("BEZGPU_FORCE_DFMA") == "1":
+            scratch = torch.empty((B, K, self.plan.L), dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            _capi.call("bez_pair_sepsq_elev_ex", self.plan.handle, _engine._ptr(cpts), B, N, 0, K,
+                       float(max_sep) ** 2, _engine._ptr(scratch), ctypes.byref(opts), _engine._stream(self.device))
         if return_device:
             return minima[0] if single else minima
         host = minima.cpu().numpy()

@@ -128,40 +128,88 @@ class PeerMinima:
     ._symmetric_memory: peer-mapped device buffers over NVLink / NVSwitch), and each rank's
     kernel stores its minima into its block of *every* rank's matrix while it computes
     (8 bytes per pair per peer next to 976 bytes per pair of HBM traffic), so no collective
-    kernel follows.  Completion = every rank has finished its kernel: a stream-ordered
-    symmetric-memory barrier.  Two matrices are rotated so that step k+1 may start while the
-    consumer still reads step k.
+    kernel follows.  Completion = every rank has finished its kernel: a symmetric-memory
+    signal-pad barrier, issued on a *side stream* behind an event, so that it never sits
+    between two pair kernels on the launch stream (round 1 issued it there: 30-40 us per
+    step of barrier latency + rank skew in front of the next persistent kernel).
+
+    Three matrices rotate.  Step k writes matrix k % 3 (locally and on every peer); before
+    a rank launches step k it waits (launch stream) for the barrier of step k-2, which says
+    that every rank has finished the kernel of step k-2 and therefore -- consumers run in
+    launch-stream order -- finished reading matrix k % 3 from step k-3.  That barrier was
+    enqueued a whole kernel earlier on a high-priority stream (it takes an SM slot at the
+    kernel boundary, next to the following persistent kernel), so the wait is free.
 
         pm = PeerMinima(B, P, device)                  # collective (rendezvous)
         local, peers = pm.targets()                    # this step's destinations
         eng.separation(cpts, E, maxSep, out=..., pairmin=local, peer_ptrs=peers)
-        gathered = pm.complete()                       # [world*B, P], valid in stream order
-    """
+        gathered = pm.complete()                       # [world*B, P]; valid after pm.wait()
+        ...
+        pm.wait()                                      # launch stream waits for the last barrier
 
-    def __init__(self, B, P, device, group=None):
+    ``layout='pairs'`` (strong scaling: one batch of B evaluations, the pair list cut into
+    ``world`` contiguous ranges): the gathered matrix is [B, P] and rank r fills columns
+    [begin_r, end_r) of every peer's matrix (``targets()`` returns views / addresses offset to
+    the range's first column; launch with ``min_pitch=P``)."""
+
+    NBUF = 3
+
+    def __init__(self, B, P, device, group=None, layout="batch"):
         import torch.distributed._symmetric_memory as symm_mem
         self.rank, self.world = world_info()
         if self.world > 8:
             raise ValueError("PeerMinima supports one NVLink domain of up to 8 GPUs")
-        self.B, self.P = int(B), int(P)
+        if layout not in ("batch", "pairs"):
+            raise ValueError("layout must be 'batch' or 'pairs'")
+        self.B, self.P, self.layout = int(B), int(P), layout
         group = dist.group.WORLD if group is None else group
-        self.buf = symm_mem.empty((2, self.world * self.B, self.P), dtype=torch.float64, device=device)
+        rows = self.world * self.B if layout == "batch" else self.B
+        self.rows = rows
+        self.buf = symm_mem.empty((self.NBUF, rows, self.P), dtype=torch.float64, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.side = torch.cuda.Stream(device=device, priority=-1)
+        self.done = [None] * self.NBUF
         self.k = 0
+        self.pair_lo, self.pair_hi = pair_range_of(self.P, self.world, self.rank) if layout == "pairs" else (0, self.P)
 
     def targets(self):
-        """(local [B, P] view, list of peer device addresses) for the current step."""
-        i = self.k & 1
-        block = (i * self.world * self.B + self.rank * self.B) * self.P * 8
-        local = self.buf[i, self.rank * self.B:(self.rank + 1) * self.B]
-        peers = [self.ptrs[r] + block for r in range(self.world) if r != self.rank]
+        """(local view, list of peer device addresses) for the current step."""
+        i = self.k % self.NBUF
+        prev2 = self.done[(self.k - 2) % self.NBUF] if self.k >= 2 else None
+        if prev2 is not None:
+            torch.cuda.current_stream().wait_event(prev2)
+        if self.layout == "batch":
+            off = (i * self.rows + self.rank * self.B) * self.P * 8
+            local = self.buf[i, self.rank * self.B:(self.rank + 1) * self.B]
+        else:
+            off = (i * self.rows * self.P + self.pair_lo) * 8
+            local = self.buf[i, :, self.pair_lo:]
+        peers = [self.ptrs[r] + off for r in range(self.world) if r != self.rank]
         return local, peers
 
     def complete(self):
-        """Stream-ordered: returns the gathered matrix of the current step once every rank's
-        kernel has finished (barrier on the symmetric-memory signal pads), then rotates."""
-        i = self.k & 1
-        self.hdl.barrier(channel=i)
+        """Issues the barrier of the current step on the side stream (behind an event recorded
+        on the launch stream) and rotates.  Returns the gathered matrix of the step; it is
+        complete once :meth:`wait` (or the event ``last_event``) has passed."""
+        i = self.k % self.NBUF
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            self.hdl.barrier(channel=i)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[i] = ev
+        self.last_event = ev
         self.k += 1
         return self.buf[i]
+
+    def wait(self):
+        """Launch stream waits until the most recent step is complete on every rank."""
+        if getattr(self, "last_event", None) is not None:
+            torch.cuda.current_stream().wait_event(self.last_event)
+
+
+def pair_range_of(P, world, rank):
+    return block_range(P, world, rank)

@@ -127,23 +127,29 @@ def test_batched_and_pair_ranges(gopt):
     assert torch.equal(pm, full.min(dim=2).values)
 
 
-def test_tensor_path_matches_dfma_path(gopt, monkeypatch):
-    """The DMMA/TMA kernels and the column-stationary DFMA kernels are two evaluations of
-    the same folded sums: values agree to rounding, per-pair minima follow their values."""
+@pytest.mark.parametrize("deg,E", [(10, 100),                       # C4 / C5: L = 121 (4 n-tile pairs)
+                                   (5, 0), (5, 10), (5, 100),      # C3 swarm: L = 11 / 21 / 111
+                                   (10, 0), (10, 30),              # C2 Example1: L = 21 / 51
+                                   (3, 10), (7, 0), (2, 0), (15, 33), (12, 103)])
+def test_tensor_path_matches_dfma_path(gopt, monkeypatch, deg, E):
+    """The DMMA/TMA kernels (every shape with L <= 128, degree <= 15) and the column-stationary
+    DFMA kernels are two evaluations of the same folded sums: values agree to rounding,
+    per-pair minima follow their values."""
     import torch
+    from optimalbeziertrajectorygeneration_b200 import _capi, engine
     from oracle.make_golden import synthetic_swarm_args
-    args, x = synthetic_swarm_args(70)
+    args, x = synthetic_swarm_args(70, deg=deg)
     b = gopt.BezOptimization(**args)
     X = x[None, :] + np.random.default_rng(3).normal(size=(3, x.size)) * 0.05
     eng = b._engine(True)
-    cpts, tf = eng.assemble(eng.upload(X), 100)
+    cpts, tf = eng.assemble(eng.upload(X), E)
     outs = {}
     for force in ("0", "1"):
         monkeypatch.setenv("BEZGPU_FORCE_DFMA", force)
-        sep = eng.separation(cpts, 100, 0.9)
+        sep = eng.separation(cpts, E, 0.9)
         pm = torch.empty(sep.shape[:2], dtype=torch.float64, device=sep.device)
-        eng.separation(cpts, 100, 0.9, pairmin=pm)
-        spd = eng.speed(cpts, tf, 100, -1.0, 25.0)
+        eng.separation(cpts, E, 0.9, pairmin=pm)
+        spd = eng.speed(cpts, tf, E, -1.0, 25.0)
         assert torch.equal(pm, sep.min(dim=2).values)
         outs[force] = (sep.cpu().numpy(), spd.cpu().numpy())
     assert relerr(outs["0"][0], outs["1"][0]) < 1e-13
@@ -233,9 +239,12 @@ def test_fused_gather_stores_on_one_gpu(gopt):
                                  finalPoints=np.ones((4, 2)))
     e2 = small._engine(True)
     c2, _ = e2.assemble(e2.upload(np.zeros((1, small.nvar))), 0)
-    with pytest.raises(Exception):                       # L = 7: outside the tensor-path shapes
-        e2.separation(c2, 0, 0.9, pairmin=torch.empty((1, 6), dtype=torch.float64, device=e2.device),
-                      peer_ptrs=[local.data_ptr()])
+    p6 = torch.empty((1, 6), dtype=torch.float64, device=e2.device)
+    x6 = torch.full((1, 6), float("nan"), dtype=torch.float64, device=e2.device)
+    s7 = e2.separation(c2, 0, 0.9, pairmin=p6, peer_ptrs=[x6.data_ptr()])     # L = 7: tensor path since round 2
+    assert torch.equal(p6, s7.min(dim=2).values) and torch.equal(x6, p6)
+    with pytest.raises(Exception):                       # L = 137: outside the tensor-path shapes
+        e2.separation(c2, 130, 0.9, pairmin=p6, peer_ptrs=[local.data_ptr()])
 
 
 def test_unaligned_and_ragged_outputs(gopt):

@@ -164,6 +164,7 @@ def test_spatial_separation_constraints():
     b = gopt.BezOptimization(numVeh=3, dimension=3, degree=4, maxSep=0.5, initPoints=init, finalPoints=fin,
                              shapeObstacles=[obs])
     x = b.generateGuess(std=0.1, seed=1)
+    b.spatial_on_limit = "nan"          # keep over-budget pairs as NaN rows + status (default: raise)
     got = b.spatialSeparationConstraints(x)
     assert got.shape == (6, 3)
     y = b.reshapeVector(x)

@@ -37,14 +37,43 @@ def _worker(rank, world, port, q):
         P = 70 * 69 // 2
         pm = sharding.PeerMinima(B, P, eng.device)
         ok = True
-        for step in range(3):
+        for step in range(5):
             local, peers = pm.targets()
-            sep = eng.separation(cpts, E, 0.9, pairmin=local, peer_ptrs=peers)
+            sep = eng.separation(cpts, E, 0.9 + 0.1 * step, pairmin=local, peer_ptrs=peers)
             gathered = pm.complete()
+            pm.wait()
             ref = torch.empty((world * B, P), dtype=torch.float64, device=eng.device)
             dist.all_gather_into_tensor(ref, sep.min(dim=2).values.contiguous())
             torch.cuda.synchronize()
             ok = ok and torch.equal(ref, gathered)
+        # back-to-back steps without a consumer in between (what bench.py does), checked at the end
+        keep = []
+        for step in range(7):
+            local, peers = pm.targets()
+            sep = eng.separation(cpts, E, 1.5 + 0.1 * step, pairmin=local, peer_ptrs=peers)
+            gathered = pm.complete()
+            keep.append(sep.min(dim=2).values.contiguous())
+        pm.wait()
+        ref = torch.empty((world * B, P), dtype=torch.float64, device=eng.device)
+        dist.all_gather_into_tensor(ref, keep[-1])
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(ref, gathered)
+        # strong-scaling layout: one batch, the pair list cut into `world` ranges, fused gather
+        # into one [B, P] matrix (min_pitch = P, pointers offset to the range's first column)
+        ps = sharding.PeerMinima(B, P, eng.device, layout="pairs")
+        Xs = x[None, :] + np.random.default_rng(99).normal(size=(B, x.size)) * 0.05      # same on every rank
+        cs, _ = eng.assemble(eng.upload(Xs), E)
+        full = torch.empty((B, P), dtype=torch.float64, device=eng.device)
+        eng.separation(cs, E, 0.9, pairmin=full, rows=False)
+        for step in range(4):
+            local, peers = ps.targets()
+            lo, hi = ps.pair_lo, ps.pair_hi
+            eng.separation(cs, E, 0.9, pair_begin=lo, npairs=hi - lo, pairmin=local, min_pitch=P,
+                           peer_ptrs=peers, rows=False)
+            g2 = ps.complete()
+        ps.wait()
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(g2, full)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

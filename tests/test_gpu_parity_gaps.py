@@ -115,7 +115,8 @@ def test_pickle_nan_vehicles_propagate(gopt, golden):
     ref_nan_rows = gs["seq_nan_rows"]                       # reference, 121 finite + 4 NaN vehicles
     yn = gs["seq_nan_y"]
     N = yn.shape[0] // 3
-    assert N > N0 and np.isnan(yn[3 * N0:]).all() and np.isfinite(yn[:3 * N0]).all()
+    # the pickle's unplanned vehicles have NaN interior control points (their end points are set)
+    assert N > N0 and np.isnan(yn[3 * N0:]).any(axis=1).all() and np.isfinite(yn[:3 * N0]).all()
     vals, pm = _raw_pair_eval(yn, N, 3, 3, 10, 0.9)
     base_vals, base_pm = _raw_pair_eval(g["seq_y"], N0, 3, 3, 10, 0.9)
     iu, ju = np.triu_indices(N, 1)
@@ -129,6 +130,27 @@ def test_pickle_nan_vehicles_propagate(gopt, golden):
     assert np.array_equal(pm[~has_nan], base_pm)
     # (the reference's finite rows are bit-identical to seq_sep_E10, checked when the fixture was made)
     assert relerr(vals[~has_nan], g["seq_sep_E10"].reshape(-1, L)) < RTOL
+
+
+@pytest.mark.parametrize("deg,E", [(10, 100), (5, 10), (10, 300)])
+def test_nan_vehicle_on_every_kernel_family(gopt, deg, E):
+    """The same property on the tensor-path shapes (L = 121), the small-L shapes and L > 128:
+    one NaN control point makes all L values and the minimum of every pair of that vehicle NaN,
+    all other pairs keep their bits."""
+    from oracle.make_golden import synthetic_swarm_args
+    from oracle import bezier_oracle as O
+    N = 41
+    args, x = synthetic_swarm_args(N, deg=deg)
+    y = O.reshape_vector(O.Model(**args), x)
+    base_vals, base_pm = _raw_pair_eval(y, N, 3, deg, E, 0.9)
+    yn = y.copy()
+    yn[3 * 17 + 1, 2] = np.nan                              # one interior control point of vehicle 17
+    vals, pm = _raw_pair_eval(yn, N, 3, deg, E, 0.9)
+    iu, ju = np.triu_indices(N, 1)
+    bad = (iu == 17) | (ju == 17)
+    assert np.isnan(vals[bad]).all() and np.isnan(pm[bad]).all()
+    assert np.array_equal(vals[~bad], base_vals[~bad]) and np.array_equal(pm[~bad], base_pm[~bad])
+    assert np.array_equal(base_pm, base_vals.min(axis=1))
 
 
 def test_example1_own_separation_closure(gopt, golden):

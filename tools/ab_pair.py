@@ -1,0 +1,61 @@
+"""A/B timing of the fused pair kernel on the C4 workload: kernel flags (BEZGPU_MMA_FLAGS:
+1 = L1 prefetch of the next tile's rows, 2 = round-1 strided tile order) x output variants.
+usage: python tools/ab_pair.py [B] [reps]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from bench import WORKLOAD, fd_batch, synthetic_swarm
+from optimalbeziertrajectorygeneration_b200 import optimization as gopt
+from optimalbeziertrajectorygeneration_b200.engine import ActiveSet, num_pairs
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+N, deg, E = WORKLOAD["N"], WORKLOAD["deg"], WORKLOAD["elev"]
+args, x = synthetic_swarm(N, deg)
+bezopt = gopt.BezOptimization(**args)
+eng = bezopt._engine(True)
+P, L = num_pairs(N), 2 * deg + E + 1
+d_x = eng.upload(fd_batch(x, B))
+out = torch.empty((B, P, L), dtype=torch.float64, device=eng.device)
+pm = torch.empty((B, P), dtype=torch.float64, device=eng.device)
+act = ActiveSet(B * P, capacity=1 << 17, device=eng.device)
+cpts, tf = eng.assemble(d_x, E)
+gb = 8.0 * B * (P * L + P + 34 * N) / 1e9
+
+
+def timeit(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in evs])
+
+
+variants = {
+    "rows+min": lambda: eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm),
+    "rows only": lambda: eng.separation(cpts, E, args["maxSep"], out=out),
+    "rows+min+mask+list": lambda: (act.reset(), eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm, active=act)),
+    "min only (no rows)": lambda: eng.separation(cpts, E, args["maxSep"], pairmin=pm, rows=False),
+}
+for flags in os.environ.get("AB_FLAGS", "0,2,1").split(","):
+    os.environ["BEZGPU_MMA_FLAGS"] = flags
+    for name, fn in variants.items():
+        ms = timeit(fn)
+        print("flags=%s %-20s mean %.4f ms  min %.4f ms  -> %.0f GB/s = %.3f of 6484.6" %
+              (flags, name, ms.mean(), ms.min(), gb / (ms.mean() * 1e-3), gb / (ms.mean() * 1e-3) / 6484.6), flush=True)
+ref = out.min(dim=2).values
+os.environ["BEZGPU_MMA_FLAGS"] = "0"
+eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm)
+print("min == row min:", bool(torch.equal(pm, out.min(dim=2).values)), " active pairs:", int((pm < 0).sum()))
