@@ -221,21 +221,64 @@ def run_reference(opts):
             "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
             "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(1), "cpu_baseline": cb,
+            "config": workload_config(), "evals_per_step_per_gpu": None, "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config(B, gather_mode="n/a"):
+def workload_config():
+    """The same dict on both arms (the driver compares them); per-arm details such as the
+    batch per step or the gather implementation are top-level keys of the line."""
     return {"workload": "C4 synthetic swarm: N=1024 vehicles, dim 3, degree 10, DEG_ELEV 100, "
                         "all 523776 pairs x 121 separation values + 1024 x 121 max-speed values per eval",
-            "evals_per_step_per_gpu": B, "sharding": "FD-perturbation batch split across ranks; "
-            "all-gather of the [B,P] per-pair minimum", "gather": gather_mode, "l2_policy": "outputs (508 MB/eval) >> 126 MB L2, "
-            "streaming stores; inputs 270 KB"}
+            "sharding": "FD-perturbation batch split across ranks; all-gather of the [B,P] per-pair minimum",
+            "l2_policy": "outputs (508 MB/eval) >> 126 MB L2, streaming stores; inputs 270 KB"}
 
 
 # --------------------------------------------------------------------------
+def _dist_env():
+    return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def _bind_to_gpu_numa_node(local):
+    """Binds this rank's host threads to the CPUs of its GPU's NUMA node (NVML affinity), so
+    that pinned staging buffers and the copy threads sit next to the GPU's PCIe root."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = int(vis.split(",")[local]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _time_events(fn, reps, torch):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b_ in evs:
+        a.record()
+        fn()
+        b_.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b_) for a, b_ in evs]))
+
+
 def run_ours(opts):
     import torch
     import torch.distributed as dist
@@ -243,69 +286,94 @@ def run_ours(opts):
     from optimalbeziertrajectorygeneration_b200 import sharding
     from optimalbeziertrajectorygeneration_b200.engine import num_pairs
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = _dist_env()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
+    numa_cpus = _bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    strong = opts.scaling == "strong"
 
     N, deg, E = WORKLOAD["N"], WORKLOAD["deg"], WORKLOAD["elev"]
     B = opts.batch
     args, x = synthetic_swarm(N, deg)
-    Xall = fd_batch(x, B * world)
-    X = Xall[rank * B:(rank + 1) * B]
+    if strong:                      # one batch of B evaluations, the pair list cut into `world` ranges
+        Xall = fd_batch(x, B)
+        X = Xall
+    else:                           # weak: every rank evaluates its own B perturbed x over all pairs
+        Xall = fd_batch(x, B * world)
+        X = Xall[rank * B:(rank + 1) * B]
     bezopt = gopt.BezOptimization(**args)
     eng = bezopt._engine(True)
     P = num_pairs(N)
     L = 2 * deg + E + 1
+    p_lo, p_hi = sharding.pair_range(N, world, rank) if strong else (0, P)
+    v_lo, v_hi = sharding.block_range(N, world, rank) if strong else (0, N)
+    Pr, Nr = p_hi - p_lo, v_hi - v_lo
     d_x = eng.upload(X)
-    out_sep = torch.empty((B, P, L), dtype=torch.float64, device=eng.device)
-    out_spd = torch.empty((B, N, L), dtype=torch.float64, device=eng.device)
-    pairmin = torch.empty((B, P), dtype=torch.float64, device=eng.device)
+    out_sep = torch.empty((B, Pr, L), dtype=torch.float64, device=eng.device)
+    out_spd = torch.empty((B, Nr, L), dtype=torch.float64, device=eng.device)
+    pairmin = torch.empty((B, Pr), dtype=torch.float64, device=eng.device)
     max_speed2 = float(args["maxSpeed"]) ** 2
 
-    # The one collective of the path: every rank ends up with the whole [world*B, P] per-pair
-    # minimum (active-pair) matrix.  Preferred: fused into the pair kernel (NVLink peer stores
-    # into symmetric memory, sharding.PeerMinima); fallback: NCCL all-gather on its own stream.
+    # The one collective of the path: every rank ends up with the whole per-pair minimum
+    # (active-pair) matrix -- [world*B, P] (weak) or [B, P] (strong).  Preferred: fused into the
+    # pair kernel (NVLink peer stores into symmetric memory, sharding.PeerMinima); fallback:
+    # NCCL all-gather on its own stream.
     gatherer, peer, gather_mode = None, None, "none (1 GPU)"
     if world > 1 and not opts.nccl_gather:
         try:
-            peer = sharding.PeerMinima(B, P, eng.device)
-            gather_mode = "fused: in-kernel NVLink peer stores into symmetric memory + signal-pad barrier"
+            peer = sharding.PeerMinima(B, P, eng.device, layout="pairs" if strong else "batch")
+            gather_mode = ("fused: in-kernel NVLink peer stores into symmetric memory; signal-pad barrier on a "
+                           "high-priority side stream, three rotating matrices")
         except Exception as e:                      # symmetric memory not available on this box
             if rank == 0:
                 print("PeerMinima unavailable (%r); falling back to NCCL all-gather" % (e,), file=sys.stderr)
-    if peer is None:
+    if peer is None and not strong:
         gatherer = sharding.PairMinimaGatherer(B, P, eng.device)
         if world > 1:
             gather_mode = "NCCL all_gather_into_tensor on a side stream"
+    if peer is None and strong and world > 1:
+        gather_mode = "NCCL padded all-gather (sharding.gather_pair_minima, mode 'pairs')"
 
     def step():
         cpts, tf = eng.assemble(d_x, E)
         if peer is not None:
             pm, peers = peer.targets()
-            eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pm, peer_ptrs=peers)
-            eng.speed(cpts, tf, E, -1.0, max_speed2, out=out_spd)
+            eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=out_sep, pairmin=pm,
+                           peer_ptrs=peers, min_pitch=P if strong else None)
+            eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=out_spd)
             return peer.complete()
+        if strong:
+            eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=out_sep, pairmin=pairmin)
+            eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=out_spd)
+            return sharding.gather_pair_minima(pairmin, mode="pairs", total=P)
         pm = gatherer.local_buffer()
         eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pm)
         eng.speed(cpts, tf, E, -1.0, max_speed2, out=out_spd)
         return gatherer.gather()
     launches_per_step = 3       # assemble, fused pair kernel (values + per-pair min), speed kernel
 
+    def finish():
+        if gatherer is not None:
+            gatherer.finish()
+        if peer is not None:
+            peer.wait()             # the last step's barrier (side stream) belongs to the timed region
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def maxreduce(v):
+        t = torch.tensor([v], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(max(3, opts.warmup)):
         step()
-    if gatherer is not None:
-        gatherer.finish()
-    if peer is not None:
-        peer.wait()
+    finish()
     sampler = ClockSampler(local, period=opts.clock_period)
     if rank == 0:
         sampler.open()
@@ -316,186 +384,321 @@ def run_ours(opts):
     ev0.record()
     for _ in range(opts.steps):
         gathered = step()
-    if gatherer is not None:
-        gatherer.finish()
-    if peer is not None:
-        peer.wait()                 # the last step's barrier (side stream) is part of the timed region
+    finish()
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+    ms = maxreduce(ev0.elapsed_time(ev1))
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # self-check of the collective (outside the timed region): the gathered matrix of the
         # last step must equal a plain NCCL all-gather of the per-rank minima, bit for bit
-        mine = gathered[rank * B:(rank + 1) * B].clone()
-        ref = torch.empty((world * B, P), dtype=torch.float64, device=eng.device)
-        dist.all_gather_into_tensor(ref, mine)
+        mine = out_sep.min(dim=2).values.contiguous()
+        if strong:
+            ref = sharding.gather_pair_minima(mine, mode="pairs", total=P)
+        else:
+            ref = torch.empty((world * B, P), dtype=torch.float64, device=eng.device)
+            dist.all_gather_into_tensor(ref, mine)
         torch.cuda.synchronize()
         assert torch.equal(ref, gathered), "gathered per-pair minima differ from the NCCL all-gather"
-        assert torch.equal(mine, out_sep.min(dim=2).values), "per-pair minima differ from the row minima"
-    ms = float(t.item())
 
-    # dominant kernel alone (pair kernel), CUDA events on its stream
+    # dominant kernel alone (pair kernel over this rank's pairs), CUDA events on its stream
     cpts, tf = eng.assemble(d_x, E)
     torch.cuda.synchronize()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(opts.steps)]
-    for a, b_ in kev:
-        a.record()
-        eng.separation(cpts, E, args["maxSep"], out=out_sep, pairmin=pairmin)
-        b_.record()
-    torch.cuda.synchronize()
-    kms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
+    kms = _time_events(lambda: eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=out_sep,
+                                              pairmin=pairmin), opts.steps, torch)
     clocks = sampler.stop() if rank == 0 else None
+    line = None
+    peak, peak_src = _peak()
+    if rank == 0:
+        alg_bytes = 8.0 * B * (Pr * L + Pr + 34 * N)    # rows + per-pair minima written, control-point rows read
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        # measured DRAM traffic of the same launch shape from the committed ncu --set full capture
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
+        if os.path.exists(tpath) and not strong:
+            tj = json.load(open(tpath))
+            if tj.get("evals_per_launch") == B:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        evals = (B if strong else B * world) * opts.steps
+        line = {"metric": "constraint+Jacobian evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s",
+                "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
+                "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": opts.scaling,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(), "evals_per_step_per_gpu": B if not strong else B / world,
+                "gather": gather_mode,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "kernel": "sq_elev_mma_kernel<10,3,PAIR,4 n-tile pairs,min,rows> (DMMA.8x8x4 stage 2, "
+                                       "TMA bulk-store epilogue)",
+                             "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                "gpu_launches": launches_per_step * opts.steps, "clocks": clocks}
+        if strong:
+            line["config"] = dict(workload_config(), sharding="one FD batch; the pair list cut into contiguous "
+                                  "ranges per rank (vehicle blocks for the speed rows); fused gather into one [B,P] matrix")
+        if numa_cpus:
+            line["host_cpus_bound_per_rank"] = numa_cpus
 
-    # end to end through the public host API (host X in pinned memory -> H2D ->
-    # kernels, every row materialised in HBM -> D2H of the step's result).
-    #  (a) evaluate_reduced: result = per-pair minima [B,P] + max-speed rows
-    #  (b) the reference-facing closures: result = the full constraint vector
+    if strong:                      # the strong-scaling line carries the device-timed figures only
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ----------------------------------------------------------------------------------
+    # End to end through the public host API: host X (pinned) -> H2D -> kernels (every row
+    # materialised in HBM) -> D2H of the step's result.
+    #  (a) evaluate_sweep_active: result = packed active-pair bitmask + compacted (pair, min)
+    #      list + per-vehicle max-speed minima and bitmask           <- the headline e2e
+    #  (b) evaluate_sweep: result = the fp64 per-pair minimum matrix + all max-speed rows
+    #  (c) evaluate_reduced: (b) one call per step, strictly serial
+    #  (d) the reference-facing closures: the full 508 MB constraint vector per x
     gopt.DEG_ELEV = E
     bezopt.zero_copy_results = True
-    nE = max(3, min(opts.steps, 20))
-    for _ in range(3):
+    nS = max(8, min(opts.steps, 40))
+    Xs = np.concatenate([X] * nS, axis=0)
+    for _ in range(2):
+        act = bezopt.evaluate_sweep_active(Xs, elev=E, chunk=B)
+    barrier()
+    t0 = time.perf_counter()
+    act = bezopt.evaluate_sweep_active(Xs, elev=E, chunk=B)
+    dt_act = maxreduce(time.perf_counter() - t0)
+    d2h_act = int((act.pair_bufs.shape[1] + act.veh_bufs.shape[1]) * 8 + B * N * 8)
+    nM = max(4, min(opts.steps, 24))
+    Xm = Xs[:nM * B]
+    for _ in range(2):
+        sw = bezopt.evaluate_sweep(Xm, elev=E, chunk=B)
+    barrier()
+    t0 = time.perf_counter()
+    sw = bezopt.evaluate_sweep(Xm, elev=E, chunk=B)
+    dt_sweep = maxreduce(time.perf_counter() - t0)
+    # the reduced result is consistent with the minimum matrix
+    flags, ev_i, pair_i, val = act.pairs(0)
+    assert np.array_equal(flags, sw["pairmin"][:B] < 0) and np.array_equal(val, sw["pairmin"][:B][flags])
+    vmin, vflags = act.vehicles(0)
+    assert np.array_equal(vmin, sw["maxspeed"][:B].reshape(B, N, L).min(axis=2))
+    nE = max(3, min(opts.steps, 10))
+    for _ in range(2):
         red = bezopt.evaluate_reduced(X, elev=E)
     barrier()
     t0 = time.perf_counter()
     for _ in range(nE):
         red = bezopt.evaluate_reduced(X, elev=E)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt_red = float(tt.item())
+    dt_red = maxreduce(time.perf_counter() - t0)
     sepf, spdf = bezopt.temporalSeparationConstraints, bezopt.maxSpeedConstraints
-    nF = 3
-    for _ in range(2):
-        r1 = sepf(X[0]); r2 = spdf(X[0])
+    nF = 2
+    r1 = sepf(X[0]); r2 = spdf(X[0])
     barrier()
     t0 = time.perf_counter()
     for s_ in range(nF):
         r1 = sepf(X[s_ % B]); r2 = spdf(X[s_ % B])
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt_full = float(tt.item())
-    # (c) the pipelined sweep API: nS chunks of B rows, copies of chunk k overlap kernels of k+1
-    nS = max(4, min(opts.steps, 24))
-    Xs = np.concatenate([X] * nS, axis=0)
-    for _ in range(2):
-        sw = bezopt.evaluate_sweep(Xs, elev=E, chunk=B)
-    barrier()
-    t0 = time.perf_counter()
-    sw = bezopt.evaluate_sweep(Xs, elev=E, chunk=B)
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt_sweep = float(tt.item())
-    assert np.array_equal(sw["pairmin"][:B], red["pairmin"]) and np.array_equal(sw["maxspeed"][-B:], red["maxspeed"])
-    e2e = {"value": nS * B * world / dt_sweep, "unit": "evals/s",
-           "h2d_bytes_per_step": int(X.size * 8),
-           "d2h_bytes_per_step": int((red["pairmin"].size + red["maxspeed"].size) * 8),
-           "steps_timed": nS,
-           "note": "BezOptimization.evaluate_sweep(X_host[steps*B, nvar], chunk=B): per step (chunk of B rows) pinned "
-                   "H2D of X -> assemble -> fused pair kernel (all P*L values written to HBM + per-pair min) -> speed "
-                   "kernel -> D2H of the per-pair minima and max-speed rows into pinned host memory; two device "
-                   "workspaces, the D2H of step k overlaps the kernels of step k+1; wall clock incl. Python",
+    dt_full = maxreduce(time.perf_counter() - t0)
+    full_bytes = int((r1.size + r2.size) * 8)
+    del r1, r2
+    e2e = {"value": nS * B * world / dt_act, "unit": "evals/s",
+           "h2d_bytes_per_step": int(X.size * 8), "d2h_bytes_per_step": d2h_act, "steps_timed": nS,
+           "active_pairs_per_eval": float(act.pair_counts().mean() / B),
+           "note": "BezOptimization.evaluate_sweep_active(X_host[steps*B, nvar], chunk=B): per step (chunk of B rows) "
+                   "pinned H2D of X -> assemble -> fused pair kernel (all P*L values written to HBM, per-pair minimum "
+                   "matrix kept in HBM, packed active bitmask + compacted (pair, min) list from the epilogue) -> speed "
+                   "kernel (rows + per-vehicle minima + bitmask) -> D2H of bitmask, list, speed minima into pinned "
+                   "host memory; two device workspaces, the D2H of step k overlaps the kernels of step k+1; wall "
+                   "clock incl. Python",
+           "minima_matrix": {"value": nM * B * world / dt_sweep, "unit": "evals/s", "steps_timed": nM,
+                             "d2h_bytes_per_step": int((sw["pairmin"][:B].size + sw["maxspeed"][:B].size) * 8),
+                             "note": "round-1 e2e: evaluate_sweep, D2H of the fp64 per-pair minimum matrix [B,P] and "
+                                     "all max-speed rows"},
            "serial_call": {"value": nE * B * world / dt_red, "unit": "evals/s", "steps_timed": nE,
                            "note": "one evaluate_reduced(X_host[B,nvar]) call per step, H2D -> kernels -> D2H "
                                    "strictly in sequence with a host synchronisation per call"},
-           "full_vector": {"value": nF * world / dt_full, "unit": "evals/s",
-                           "d2h_bytes_per_eval": int((r1.size + r2.size) * 8),
+           "full_vector": {"value": nF * world / dt_full, "unit": "evals/s", "d2h_bytes_per_eval": full_bytes,
                            "note": "temporalSeparationConstraints(x)+maxSpeedConstraints(x) returning the full "
                                    "508 MB constraint vector to host memory (PCIe-bound)"}}
     gopt.DEG_ELEV = 0
+    bezopt._sweep_ws = bezopt._active_ws = bezopt.workspace = None
+    del sw, act, red
+    torch.cuda.empty_cache()
 
     # Sparse-aware FD sweep: the whole Jacobian of the separation block of ONE x
     # (what SLSQP obtains from nvar+1 = 27 649 full evals) in closed form, sweep layout
     # [variable][partner curve][L] = only the rows that depend on the variable (27.4 GB).
     sweep = None
     if not opts.no_sweep:
-        torch.cuda.empty_cache()
         J = eng.jac_separation(x, E, dense=False)
         for _ in range(2):
             eng.jac_separation(x, E, dense=False, out=J)
         torch.cuda.synchronize()
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
-        for _ in range(3):
-            eng.jac_separation(x, E, dense=False, out=J)
-        b_.record()
-        torch.cuda.synchronize()
-        sms = a_.elapsed_time(b_) / 3
+        sms = _time_events(lambda: eng.jac_separation(x, E, dense=False, out=J), 3, torch)
         sweep = {"value": (bezopt.nvar + 1) * world / (sms * 1e-3), "unit": "evals/s",
                  "ms_per_jacobian": sms, "bytes_per_jacobian": int(J.numel() * 8),
+                 "hbm_frac": int(J.numel() * 8) / (sms * 1e-3) / 1e9 / peak,
                  "note": "closed-form FD Jacobian of the separation block of one x (all %d variables x %d partner "
                          "curves x %d values), equivalent to nvar+1 full evals of the reference; every rank "
                          "computes the Jacobian of its own x" % (bezopt.nvar, N - 1, L)}
         del J
         torch.cuda.empty_cache()
+    del out_sep, out_spd, pairmin
+    torch.cuda.empty_cache()
+
+    # BASELINE configs[4] (C5) and configs[1], [2] (C2 Example1, C3 swarm) in the same line
+    c5 = None if opts.no_c5 else c5_measure(opts, world, rank, local, steps=max(3, min(opts.steps, 10)))
+    slsqp = None
+    if rank == 0 and not opts.no_slsqp:
+        slsqp = slsqp_measure(full=opts.slsqp_full)
+    barrier()
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = json.load(open(peaks_path))["hbm_gbs"]
-            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        alg_bytes = 8.0 * B * (P * L + P + 34 * N)      # rows + per-pair minima written, control-point rows read
-        achieved = alg_bytes / (kms * 1e-3) / 1e9
-        # measured DRAM traffic of the same launch shape from the committed ncu --set full capture
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if tj.get("evals_per_launch") == B:
-                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-        evals = B * world * opts.steps
-        line = {"metric": "constraint+Jacobian evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s",
-                "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
-                "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(B, gather_mode),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                             "kernel": "sq_elev_mma_kernel<10,3,PAIR,min> (DMMA.8x8x4 stage 2, TMA bulk-store epilogue)",
-                             "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
-                "e2e": e2e, "gpu_launches": launches_per_step * opts.steps, "clocks": clocks}
+        line["e2e"] = e2e
         if sweep is not None:
-            sweep["hbm_frac"] = sweep["bytes_per_jacobian"] / (sweep["ms_per_jacobian"] * 1e-3) / 1e9 / peak
             line["jacobian_sweep"] = sweep
+        if c5 is not None:
+            line["c5"] = c5
+        if slsqp is not None:
+            line["slsqp_c2"], line["slsqp_c3"] = slsqp["c2"], slsqp["c3"]
         if world == 1 and not opts.no_cpu:
             cb, _ = cpu_baseline(args, x, E, target_seconds=12.0)
             line["cpu_baseline"] = cb
+            pyref = cpu_baseline_python(args, x, E)
+            if pyref is not None:
+                line["cpu_baseline_python"] = pyref
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------
-def run_c5(opts):
-    """Secondary workload (BASELINE.json configs[4], SURVEY 8(d) "C5"): independent Dubins
-    time-optimal problems (1 vehicle, degree 10, DEG_ELEV 100, 16 point obstacles each);
-    one step = one FD sweep (nvar+1 = 16 evals) of every problem of this rank's block.
-    Problems are dealt out in contiguous blocks (no collective).  Not the headline line:
-    run with `--workload c5`."""
+def cpu_baseline_python(args, x, E, npairs=2048):
+    """The unmodified Python reference (numpy + numba) timed on this host, when a copy of it
+    travelled with the repository (baseline/_ref, written by __graft_entry__.build() in the
+    authoring container; git-ignored).  One thread, a bounded sample: the first vehicles of the
+    C4 swarm whose pair count reaches `npairs`, through the reference's own
+    _temporalSeparationConstraints."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_root, "bezier.py")):
+        return None
+    try:
+        from oracle import ref_loader
+        from oracle import bezier_oracle as O
+        ref_loader.REFERENCE_ROOT = ref_root
+        ref = ref_loader.load()
+        m = O.Model(**args)
+        y = O.reshape_vector(m, x)
+        nveh = 2
+        while nveh * (nveh - 1) // 2 < npairs:
+            nveh += 1
+        ys = np.ascontiguousarray(y[:nveh * 3])
+        ref.optimization.DEG_ELEV = E
+        try:
+            ref.optimization._temporalSeparationConstraints(ys, nveh, 3, m.maxSep)      # JIT + table caches
+            t0 = time.perf_counter()
+            c = ref.optimization._temporalSeparationConstraints(ys, nveh, 3, m.maxSep)
+            dt = time.perf_counter() - t0
+        finally:
+            ref.optimization.DEG_ELEV = 0
+        pairs = nveh * (nveh - 1) // 2
+        P = m.numVeh * (m.numVeh - 1) // 2
+        return {"value": 1.0 / (dt / pairs * P), "unit": "evals/s", "cores": 1, "kind": "reference",
+                "us_per_pair": 1e6 * dt / pairs,
+                "sample": "%d pairs (the first %d vehicles of the C4 swarm) through the unmodified reference's "
+                          "_temporalSeparationConstraints (numpy + numba, 1 thread, warm caches), %.2f s; extrapolated "
+                          "linearly to the %d pairs of one eval (speed rows not included)" % (pairs, nveh, dt, P),
+                "check": float(np.abs(np.asarray(c)).max())}
+    except Exception as e:          # pragma: no cover
+        return {"unavailable": repr(e)}
+
+
+# --------------------------------------------------------------------------
+def _example1_problem(mod, veh_only=False):
+    kw = dict(numVeh=2, dimension=2, degree=10, minimizeGoal='TimeOpt', maxSep=1, maxSpeed=5, maxAngRate=1,
+              initPoints=[(0, 5), (3, 0)], finalPoints=[(8, 4), (7, 10)], initSpeeds=[1, 1], finalSpeeds=[1, 1],
+              initAngs=[0, np.pi / 2], finalAngs=[0, np.pi / 2])
+    if not veh_only:
+        kw["pointObstacles"] = [[3, 2], [6, 7]]
+    return kw
+
+
+def slsqp_measure(full=False):
+    """BASELINE configs[1] and [2]: wall seconds of scipy.optimize.minimize(method='SLSQP') with
+    (i) the GPU closures (SciPy forms the Jacobians with nvar+1 calls), (ii) the GPU closures +
+    their *_jac closures + objectiveFunction_jac (one batched launch per Jacobian), (iii) the
+    numpy restatement of the reference's callables on the host (oracle.bezier_oracle).
+    C2 = Examples/Example1_DubinsCarTimeOptimal.py:95-148 at elev 0 (reference: tf =
+    2.4276431891903045, nit 22); C3 = Examples/SwarmOfAerialVehicles.py:137-166 (36 vehicles,
+    nvar 432, one separation constraint block of 6930 values).  The host arm of C3 costs minutes
+    per run, so unless --slsqp-full is given arms (i) and (iii) of C3 are capped at `cap` major
+    iterations (same cap for both; arm (ii) always runs to convergence)."""
+    import scipy.optimize as sop
+    from oracle import bezier_oracle as O
+    from optimalbeziertrajectorygeneration_b200 import optimization as gopt
+
+    def run(fun, x0, cons, jac=None, maxiter=250):
+        t0 = time.perf_counter()
+        res = sop.minimize(fun, x0=x0, method='SLSQP', jac=jac, constraints=cons, options={'maxiter': maxiter})
+        return {"wall_s": time.perf_counter() - t0, "fun": float(res.fun), "nit": int(res.nit),
+                "nfev": int(res.nfev), "success": bool(res.success), "maxiter": maxiter}
+
+    out = {}
+    # ---- C2 ----
+    gopt.DEG_ELEV = 0
+    b = gopt.BezOptimization(**_example1_problem(gopt))
+    vo = gopt.BezOptimization(**_example1_problem(gopt, veh_only=True))     # the example's own separation closure
+    x0 = b.generateGuess(std=0)
+    last = lambda v: v[-1]
+    cons = [{'type': 'ineq', 'fun': vo.temporalSeparationConstraints}, {'type': 'ineq', 'fun': b.maxSpeedConstraints},
+            {'type': 'ineq', 'fun': b.maxAngularRateConstraints}, {'type': 'ineq', 'fun': last}]
+    consj = [dict(c) for c in cons]
+    consj[0]['jac'] = vo.temporalSeparationConstraints_jac
+    consj[1]['jac'] = b.maxSpeedConstraints_jac
+    consj[2]['jac'] = b.maxAngularRateConstraints_jac
+    run(b.objectiveFunction, x0, consj, jac=b.objectiveFunction_jac, maxiter=2)          # warm-up (plans, tables)
+    c2 = {"gpu_closures": run(b.objectiveFunction, x0, cons),
+          "gpu_closures_jac": run(b.objectiveFunction, x0, consj, jac=b.objectiveFunction_jac)}
+    mo = O.Model(**_example1_problem(gopt))
+    fo, fv = O.make_callables(mo, 0), O.make_callables(O.Model(**_example1_problem(gopt, veh_only=True)), 0)
+    c2["host_oracle"] = run(last, x0, [{'type': 'ineq', 'fun': fv['sep']}, {'type': 'ineq', 'fun': fo['maxspeed']},
+                                       {'type': 'ineq', 'fun': fo['angrate']}, {'type': 'ineq', 'fun': last}])
+    c2["reference_tf"] = 2.4276431891903045
+    c2["problem"] = "Example1: 2 Dubins vehicles, degree 10, time-optimal, nvar 29, elev 0; constraints 21 + 42 + 82 + 1"
+    out["c2"] = c2
+    # ---- C3 ----
+    g = np.load(os.path.join(ROOT, "tests", "golden", "constraints.npz"))
+    kw = dict(numVeh=36, dimension=3, degree=5, minimizeGoal='Euclidean', maxSep=0.9,
+              initPoints=g["swarm_initPts"], finalPoints=g["swarm_finalPts"])
+    b = gopt.BezOptimization(**kw)
+    x0 = g["swarm_x0"]
+    cons = [{'type': 'ineq', 'fun': b.temporalSeparationConstraints}]
+    consj = [{'type': 'ineq', 'fun': b.temporalSeparationConstraints, 'jac': b.temporalSeparationConstraints_jac}]
+    run(b.objectiveFunction, x0, consj, jac=b.objectiveFunction_jac, maxiter=1)
+    cap = 250 if full else 3
+    c3 = {"gpu_closures_jac": run(b.objectiveFunction, x0, consj, jac=b.objectiveFunction_jac),
+          "gpu_closures": run(b.objectiveFunction, x0, cons, maxiter=cap)}
+    mo = O.Model(**kw)
+    fo = O.make_callables(mo, 0)
+    obj = lambda v: O.euclidean_objective(O.reshape_vector(mo, v), 36, 3)
+    c3["host_oracle"] = run(obj, x0, [{'type': 'ineq', 'fun': fo['sep']}], maxiter=cap)
+    t0 = time.perf_counter()
+    Jt = b.temporalSeparationConstraints_jac(x0)
+    c3["jacobian_ms_gpu"] = 1e3 * (time.perf_counter() - t0)
+    c3["jacobian_shape"] = list(Jt.shape)
+    c3["problem"] = ("SwarmOfAerialVehicles: 36 vehicles, 3-D, degree 5, nvar 432, DEG_ELEV 0, 630 pairs x 11 values; "
+                     "objective at x0 = 382.0101330471013")
+    out["c3"] = c3
+    return out
+
+
+# --------------------------------------------------------------------------
+def c5_measure(opts, world, rank, local, steps):
+    """BASELINE.json configs[4] (SURVEY 8(d) "C5"): independent Dubins time-optimal problems
+    (1 vehicle, degree 10, DEG_ELEV 100, 16 point obstacles each); one step = one FD sweep
+    (nvar+1 = 16 evals) of every problem of this rank's block.  Problems are dealt out in
+    contiguous blocks (no collective).  Returns the measurement dict on rank 0."""
     import torch
     import torch.distributed as dist
     from optimalbeziertrajectorygeneration_b200 import optimization as gopt
     from optimalbeziertrajectorygeneration_b200 import sharding
     from optimalbeziertrajectorygeneration_b200.batch import ProblemBatch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     Mtot = opts.problems * world                                # weak scaling: problems per rank fixed
     lo, hi = sharding.block_range(Mtot, world, rank)
     M, E, nobs, deg = hi - lo, 100, 16, 10
@@ -520,17 +723,12 @@ def run_c5(opts):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, opts.warmup)):
+    for _ in range(3):
         F = step()
-    sampler = ClockSampler(local, period=opts.clock_period)
-    if rank == 0:
-        sampler.open()
     barrier()
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(opts.steps):
+    for _ in range(steps):
         F = step()
     ev1.record()
     barrier()
@@ -538,7 +736,6 @@ def run_c5(opts):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     # per-block kernel times (CUDA events) to name the dominant kernel
     cpts, tf = pb.eng.assemble(d_X, E, obst_sets=pb.d_obst, evals_per_set=nv1)
     parts = {}
@@ -546,36 +743,56 @@ def run_c5(opts):
                      ("maxspeed", lambda: pb.eng.speed(cpts, tf, E, -1.0, 9.0)),
                      ("angrate", lambda: pb.eng.angrate(cpts, tf, E, -1.0, (np.pi / 2) ** 2))):
         fn()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(3):
-            fn()
-        b_.record()
-        torch.cuda.synchronize()
-        parts[name] = a.elapsed_time(b_) / 3
+        parts[name] = _time_events(fn, 3, torch)
+    del F, cpts, tf
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    L, A = 2 * deg + E + 1, 4 * (deg + E) + 1
+    evals = M * nv1 * world * steps
+    alg_eval = 8.0 * (pb.npairs_x * L + L + A + 2 * (deg + 1) + 1)       # 20 168 B
+    peak, _ = _peak()
+    m_ = deg + E
+    fma_eval = 4 * (m_ + 1) ** 2 + 2 * (2 * m_ + 1) ** 2                    # 146 966 MAC
+    return {"value": evals / (ms * 1e-3), "unit": "evals/s", "problems_per_gpu": M, "evals_per_problem": nv1,
+            "steps": steps, "ms_per_step": ms / steps, "kernel_ms": parts,
+            "hbm_frac_whole_step": alg_eval * M * nv1 / (ms / steps * 1e-3) / 1e9 / peak,
+            "angrate_fp64_frac": fma_eval * M * nv1 / (parts["angrate"] * 1e-3) / (64 * 148 * 1.965e9),
+            "separation_hbm_frac": 8.0 * pb.npairs_x * L * M * nv1 / (parts["separation"] * 1e-3) / 1e9 / peak,
+            "gpu_launches": 4 * steps,
+            "workload": "C5 synthetic Dubins batch: %d problems per GPU x (nvar+1 = %d) FD points, 1 vehicle + 16 "
+                        "point obstacles, dim 2, degree 10, DEG_ELEV 100: 16 separation rows + max-speed row + "
+                        "angular-rate row per eval; contiguous blocks of problems per rank, no collective" % (M, nv1),
+            "note": "fp64 peak = 64 FMA/clk/SM x 148 SMs x 1.965 GHz (tools/pipe_bench.cu)"}
+
+
+def run_c5(opts):
+    """`--workload c5`: the C5 measurement as its own line (the default line carries it as the key `c5`)."""
+    import torch
+    import torch.distributed as dist
+    world, rank, local = _dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local, period=opts.clock_period)
     if rank == 0:
-        L, A = 2 * deg + E + 1, 4 * (deg + E) + 1
-        evals = M * nv1 * world * opts.steps
-        alg_eval = 8.0 * (pb.npairs_x * L + L + A + 2 * (deg + 1) + 1)       # 20 168 B
-        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
-            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        m_ = deg + E
-        fma_eval = 4 * (m_ + 1) ** 2 + 2 * (2 * m_ + 1) ** 2                    # 146 966 MAC
-        line = {"metric": "constraint+Jacobian evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s",
-                "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup), "ms_per_step": ms / opts.steps,
+        sampler.open()
+        sampler.start()
+    c5 = c5_measure(opts, world, rank, local, steps=opts.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, _ = _peak()
+        line = {"metric": "constraint+Jacobian evals/sec", "value": c5["value"], "unit": "evals/s",
+                "n_gpus": world, "steps": opts.steps, "warmup": 3, "ms_per_step": c5["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C5 synthetic Dubins batch: %d problems per GPU x (nvar+1 = %d) FD points, "
-                                       "1 vehicle + 16 point obstacles, dim 2, degree 10, DEG_ELEV 100: 16 separation "
-                                       "rows + max-speed row + angular-rate row per eval" % (M, nv1),
-                           "problems_per_gpu": M, "sharding": "contiguous blocks of problems per rank, no collective"},
-                "kernel_ms": parts,
+                "config": {"workload": c5["workload"]}, "kernel_ms": c5["kernel_ms"],
                 "roofline": {"bound": "fp64 (angular rate) / hbm (separation rows)",
-                             "hbm_frac_whole_step": alg_eval * M * nv1 / (ms / opts.steps * 1e-3) / 1e9 / peak,
-                             "angrate_fp64_frac": fma_eval * M * nv1 / (parts["angrate"] * 1e-3) / (64 * 148 * 1.965e9),
-                             "separation_hbm_frac": 8.0 * pb.npairs_x * L * M * nv1 / (parts["separation"] * 1e-3) / 1e9 / peak,
-                             "peak": peak, "unit": "GB/s",
-                             "note": "fp64 peak = 64 FMA/clk/SM x 148 SMs x 1.965 GHz (tools/pipe_bench.cu)"},
-                "gpu_launches": 4 * opts.steps, "clocks": clocks}
+                             "hbm_frac_whole_step": c5["hbm_frac_whole_step"],
+                             "angrate_fp64_frac": c5["angrate_fp64_frac"],
+                             "separation_hbm_frac": c5["separation_hbm_frac"], "peak": peak, "unit": "GB/s",
+                             "note": c5["note"]},
+                "gpu_launches": c5["gpu_launches"], "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -596,6 +813,13 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4 = the headline swarm (default); c5 = batch of independent Dubins problems")
     ap.add_argument("--problems", type=int, default=8192, help="c5: problems per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): B evals per GPU per step; strong: one batch of B evals, the pair list "
+                         "cut into contiguous ranges per rank")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 key of the default line")
+    ap.add_argument("--no-slsqp", action="store_true", help="skip the slsqp_c2 / slsqp_c3 keys")
+    ap.add_argument("--slsqp-full", action="store_true",
+                    help="run every SLSQP arm of C3 to convergence (the host arm takes minutes)")
     opts = ap.parse_args()
     if opts.impl == "reference":
         run_reference(opts)

@@ -53,3 +53,28 @@ def test_clock_sampler_reports_missing_nvml():
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
     if out["samples"] == 0:
         assert out["sm_mhz"] is None
+
+
+def test_both_arms_share_one_config_dict():
+    """The driver compares `config` of the two arms: per-arm details live outside it."""
+    sys.path.insert(0, ROOT)
+    import bench
+    cfg = bench.workload_config()
+    assert set(cfg) == {"workload", "sharding", "l2_policy"}
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["config"] == cfg
+
+
+def test_python_reference_leg_when_staged():
+    """cpu_baseline_python times the unmodified reference from baseline/_ref (staged by
+    __graft_entry__.build() where /root/reference exists); absent copy -> None."""
+    sys.path.insert(0, ROOT)
+    import bench
+    args, x = bench.synthetic_swarm(64, 10)
+    out = bench.cpu_baseline_python(args, x, 100, npairs=256)
+    if not os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "bezier.py")):
+        assert out is None
+        return
+    assert out["kind"] == "reference" and out["cores"] == 1 and out["value"] > 0
+    assert 1.0 < out["us_per_pair"] < 5000.0
