@@ -622,7 +622,8 @@ def slsqp_measure(full=False):
     """BASELINE configs[1] and [2]: wall seconds of scipy.optimize.minimize(method='SLSQP') with
     (i) the GPU closures (SciPy forms the Jacobians with nvar+1 calls), (ii) the GPU closures +
     their *_jac closures + objectiveFunction_jac (one batched launch per Jacobian), (iii) the
-    numpy restatement of the reference's callables on the host (oracle.bezier_oracle).
+    restatement of the reference's callables on the host (C2: oracle.bezier_oracle, numpy;
+    C3: oracle/bezier_oracle.c behind numpy's reshapeVector).
     C2 = Examples/Example1_DubinsCarTimeOptimal.py:95-148 at elev 0 (reference: tf =
     2.4276431891903045, nit 22); C3 = Examples/SwarmOfAerialVehicles.py:137-166 (36 vehicles,
     nvar 432, one separation constraint block of 6930 values).  The host arm of C3 costs minutes
@@ -673,10 +674,14 @@ def slsqp_measure(full=False):
     cap = 250 if full else 3
     c3 = {"gpu_closures_jac": run(b.objectiveFunction, x0, consj, jac=b.objectiveFunction_jac),
           "gpu_closures": run(b.objectiveFunction, x0, cons, maxiter=cap)}
+    # host arm: the plain-C restatement (oracle/bezier_oracle.c, all host threads) behind numpy's
+    # reshapeVector -- the numpy restatement needs 0.2 s per eval here (340 s for 3 iterations)
+    from oracle import c_oracle as C
     mo = O.Model(**kw)
-    fo = O.make_callables(mo, 0)
     obj = lambda v: O.euclidean_objective(O.reshape_vector(mo, v), 36, 3)
-    c3["host_oracle"] = run(obj, x0, [{'type': 'ineq', 'fun': fo['sep']}], maxiter=cap)
+    hsep = lambda v: C.temporal_separation(O.reshape_vector(mo, v), 36, 3, 0.9, 0)
+    c3["host_oracle"] = run(obj, x0, [{'type': 'ineq', 'fun': hsep}], maxiter=cap)
+    c3["host_oracle"]["threads"] = C.max_threads()
     t0 = time.perf_counter()
     Jt = b.temporalSeparationConstraints_jac(x0)
     c3["jacobian_ms_gpu"] = 1e3 * (time.perf_counter() - t0)

@@ -40,7 +40,15 @@ extern "C" {
 #define BEZ_ENOMEM       (-2)   /* host allocation failed              */
 #define BEZ_EUNSUPPORTED (-3)   /* degree / dimension out of range     */
 
-#define BEZ_MAX_DEGREE    24    /* n   <= 24 for the constraint kernels */
+/* Degree limits (one place; INTEGRATION.md section 4 quotes these):
+ *   plans and the fused constraint / objective kernels   n <= BEZ_MAX_DEGREE      = 16
+ *   the fp64 tensor-path variants of those kernels        n <= BEZ_MAX_DEGREE_MMA  = 15, L <= 128, dim >= 2
+ *                                                         (other shapes run the DFMA kernels)
+ *   closed-form Jacobian kernels                          n <= BEZ_MAX_DEGREE_JAC  = 12
+ *   angular rate                                          n + elev <= 250 (tensor path <= 127) */
+#define BEZ_MAX_DEGREE      16
+#define BEZ_MAX_DEGREE_MMA  15
+#define BEZ_MAX_DEGREE_JAC  12
 #define BEZ_MAX_GEOM_PTS  32    /* n+1 <= 32 for split/GJK/minDist      */
 
 typedef struct bez_plan bez_plan;

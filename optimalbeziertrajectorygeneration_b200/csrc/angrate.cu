@@ -548,6 +548,255 @@ __global__ void __launch_bounds__(32 * kWarpsW, 4) angrate_warp2_kernel(const An
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fourth generation: the Bernstein products on the fp64 tensor path (DMMA.8x8x4), operands in
+// registers, squares at half cost.
+//
+// ncu on the third generation (profiles/r01_ncu_angrate_warp_kernel.txt): L1 data pipe 85 %,
+// fp64 pipe 49 % -- the sliding-window convolution streams its operands through LDS.  A
+// convolution c_k = sum_i a_i b_{k-i} has no shared operand between outputs, but cut into blocks
+// of 8 it becomes a sum of 8 x 8 outer products: with A_u = (a_{8u+g})_g, B_v = (b_{8v+j})_j,
+//     C_w[g][j] = sum_u a_{8u+g} b_{8(w-u)+j}            (an 8 x U times U x 8 GEMM over u)
+//     c_{8w+s}  = sum_{g+j=s} C_w[g][j]  (+ the part of C_{w-1} with g + j = s + 8)
+// One DMMA covers four u; in fragment form lane (g,t) needs a_{8(4q+t)+g} for the q-th k-step
+// (independent of w) and b_{8(w-4q-t)+g} (a function of w - 4q): the whole of a and b lives in
+// U/4 + U + 3 registers per lane and NO operand is loaded inside the product loops (all loop
+// bounds are compile-time, every register index is static).
+// Squares (three of the four product groups: x'x' + y'y', NUM^2, DEN^2): the outer products of
+// (u, v) and (v, u) are transposes of each other and have the same anti-diagonal sums, so only
+// u < w/2 is computed (plus half of the diagonal block u = w/2); the result is half the true
+// value, an exact scaling that cancels in NUM^2 / DEN^2 and is undone for DEN by an exact x 2.
+// Anti-diagonal sums: the C fragments of two blocks at a time are scattered into a 32-row ring
+// Z[row = k mod 32][slot = g] in shared memory (every slot is written exactly once per output row:
+// slots g <= s by block w, g > s by block w - 1), then 16 lanes sum the 16 finished rows (ring_pair).
+// Per vehicle 482 DMMA + 84 ring passes instead of 4600 warp-wide DFMA + 9000 LDS.
+// Instantiated per block count U1 = ceil((m+1)/8) (U2 = 2 U1 blocks for the degree-2m curves).
+constexpr int kMmaWarps = 4;
+constexpr int kMmaGuard = 32;                   // zeros on both sides of every operand row (doubles)
+constexpr int kRingPitch = 10;                  // doubles per ring row (8 slots + 2 pad)
+constexpr int kRingDoubles = 32 * kRingPitch;
+
+__device__ __forceinline__ void ang_dmma(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int U> struct ConvRegs {
+    double a[(U + 3) / 4];          // a[q] = v[8 (4q + t) + g]
+    double b[U + 3];                // b[d] = v[8 (d - t) + g]   (zero outside the row: guards)
+};
+template <int U>
+__device__ __forceinline__ void conv_load(ConvRegs<U> &R, const double *va, const double *vb, int g, int t) {
+#pragma unroll
+    for (int q = 0; q < (U + 3) / 4; ++q) R.a[q] = va[8 * (4 * q + t) + g];
+#pragma unroll
+    for (int d = 0; d < U + 3; ++d) R.b[d] = vb[8 * (d - t) + g];
+}
+// One k-step (blocks u = 4Q .. 4Q+3) of block W, if it lies in the block range of W:
+//   general product: u in [max(0, W-U+1), min(U-1, W)]
+//   SYM (HALF of a square): u < W/2 at weight 1, the diagonal block u = W/2 (W even) at weight 1/2
+template <int U, int W, bool SYM>
+__device__ __forceinline__ void conv_step(double &c0, double &c1, const ConvRegs<U> &R, int Q, int t) {
+    constexpr int ulo = W - (U - 1) > 0 ? W - (U - 1) : 0;
+    constexpr int uhi = SYM ? W / 2 : (W < U - 1 ? W : U - 1);
+    if (W < 2 * U - 1 && ulo <= uhi && uhi <= U - 1 && Q >= ulo / 4 && Q <= uhi / 4) {
+        double bq = R.b[W - 4 * Q];
+        if (SYM && Q == uhi / 4) {                       // boundary k-step: drop u > W/2, halve u = W/2 (W even)
+            constexpr int ub = uhi % 4;
+            if (W % 2 == 0) bq = t > ub ? 0.0 : (t == ub ? 0.5 * bq : bq);
+            else bq = t > ub ? 0.0 : bq;
+        }
+        ang_dmma(c0, c1, R.a[Q], bq);
+    }
+}
+
+// C fragments of the blocks W and W + 1 (two independent accumulator chains, k-steps interleaved: a
+// dependent DMMA costs ~26 cycles, an independent one 16)
+template <int U, bool SYM, bool TWO, int W>
+__device__ __forceinline__ void conv_pair(double (&cA)[2], double (&cB)[2], const ConvRegs<U> &R1,
+                                          const ConvRegs<U> &R2, int t) {
+    cA[0] = cA[1] = cB[0] = cB[1] = 0.0;
+#pragma unroll
+    for (int Q = 0; Q < (U + 3) / 4; ++Q) {
+        conv_step<U, W, SYM>(cA[0], cA[1], R1, Q, t);
+        conv_step<U, W + 1, SYM>(cB[0], cB[1], R1, Q, t);
+        if (TWO) {
+            conv_step<U, W, SYM>(cA[0], cA[1], R2, Q, t);
+            conv_step<U, W + 1, SYM>(cB[0], cB[1], R2, Q, t);
+        }
+    }
+}
+
+// Ring pass of the block pair (W, W + 1), W even: scatter both C fragments into the 32-row ring
+// (row = k mod 32, slot = g: every slot of an output row is written exactly once -- slots g <= s by
+// the block the row belongs to, g > s by the block before it), then lanes 0..15 sum the 16 finished
+// rows 8W .. 8W+15 and return c_{8W + lane}.
+// Row pitch 10 doubles: the 16 lanes of a half-warp (rows R0 + g + 2t, slot g) hit 16 distinct 8-byte
+// banks (11 g + 4 t mod 16) -- with pitch 8 every STS was a 4-way conflict and the L1 data pipe sat at
+// 96 % (profiles/r02_ncu_angrate_mma_first.txt); the row sums use LDS.128 with 16 active lanes (two
+// wavefronts each) and no shuffles, because SHFL shares the L1 data pipe that binds this kernel.
+template <int W>
+__device__ __forceinline__ double ring_pair(double *Z, const double (&cA)[2], const double (&cB)[2], int g, int t,
+                                            int lane) {
+    const int k0 = 8 * W + g + 2 * t;
+    Z[(k0 & 31) * kRingPitch + g] = cA[0];
+    Z[((k0 + 1) & 31) * kRingPitch + g] = cA[1];
+    Z[((k0 + 8) & 31) * kRingPitch + g] = cB[0];
+    Z[((k0 + 9) & 31) * kRingPitch + g] = cB[1];
+    __syncwarp();
+    double s = 0.0;
+    if (lane < 16) {
+        const double2 *zr = reinterpret_cast<const double2 *>(Z + (((8 * W) & 31) + lane) * kRingPitch);
+        const double2 v0 = zr[0], v1 = zr[1], v2 = zr[2], v3 = zr[3];
+        s = ((v0.x + v0.y) + (v1.x + v1.y)) + ((v2.x + v2.y) + (v3.x + v3.y));
+    }
+    __syncwarp();                                        // rows 8W .. 8W+6 are rewritten by the next pair
+    return s;
+}
+
+// dst[8W + r] = scale * (conv(a1, b1) + conv(a2, b2))_{8W + r} for all blocks W = 0 .. 2U-1, two blocks
+// per step; the DMMAs of the next pair are issued before the ring pass of this one (its STS -> barrier
+// -> LDS chain is pure latency).  CLEAR: the ring rows 0..6 must be zero when a product starts ("block
+// -1"); the all-zero last block 2U-1 of the previous product leaves them zero iff U is even.
+template <int U, bool SYM, bool TWO, bool CLEAR, int W = 0>
+__device__ __forceinline__ void conv_all(const ConvRegs<U> &R1, const ConvRegs<U> &R2, double *Z, double *dst,
+                                         double scale, int g, int t, int lane, double a0 = 0.0, double a1 = 0.0,
+                                         double b0 = 0.0, double b1 = 0.0) {
+    if constexpr (W < 2 * U) {
+        double cA[2] = {a0, a1}, cB[2] = {b0, b1};
+        if constexpr (W == 0) {
+            conv_pair<U, SYM, TWO, 0>(cA, cB, R1, R2, t);
+            if constexpr (CLEAR) {
+                __syncwarp();                                // the previous product's last ring reads
+#pragma unroll
+                for (int i = 0; i < kRingDoubles / 32; ++i) Z[32 * i + lane] = 0.0;
+                __syncwarp();
+            }
+        }
+        double nA[2] = {0.0, 0.0}, nB[2] = {0.0, 0.0};
+        if constexpr (W + 2 < 2 * U) conv_pair<U, SYM, TWO, W + 2>(nA, nB, R1, R2, t);
+        const double s = ring_pair<W>(Z, cA, cB, g, t, lane);
+        if (lane < 16) dst[8 * W + lane] = s * scale;
+        conv_all<U, SYM, TWO, CLEAR, W + 2>(R1, R2, Z, dst, scale, g, t, lane, nA[0], nA[1], nB[0], nB[1]);
+    }
+}
+
+template <int U1>
+__global__ void __launch_bounds__(32 * kMmaWarps, 4) angrate_mma_kernel(const AngArgs A) {
+    constexpr int U2 = 2 * U1;
+    constexpr int ROW1 = kMmaGuard + 8 * U1 + kMmaGuard + 8;       // operand row of a degree-m curve
+    constexpr int ROW2 = kMmaGuard + 8 * U2 + kMmaGuard + 8;       // ... of a degree-2m curve
+    constexpr int PER_WARP = 4 * ROW1 + 2 * ROW2 + kRingDoubles;
+    static_assert(4 * ROW1 >= 16 * U2 && 2 * ROW2 >= 16 * U2, "result rows alias the dead operand rows");
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long item = (long long)blockIdx.x * kMmaWarps + warp;
+    if (item >= (long long)A.B * A.nveh) return;                 // whole warp; no block-wide barriers below
+    const int m = A.m, n = A.n, m1 = m + 1, L4 = 4 * m + 1;
+    double *base = sm + (size_t)warp * PER_WARP;
+    double *XD = base + kMmaGuard, *YD = XD + ROW1, *XDN = YD + ROW1, *YDD = XDN + ROW1;   // XDN = -x''
+    double *NUM = base + 4 * ROW1 + kMmaGuard, *DEN = NUM + ROW2;
+    double *Z = base + 4 * ROW1 + 2 * ROW2;                       // [32][8] ring
+    double *N2 = base;                                            // NUM^2 (16 U2 doubles) over the dead degree-m rows
+    double *D2 = base + 4 * ROW1;                                 // DEN^2 over the dead NUM | DEN rows
+    double *px = NUM, *py = NUM + 8 * U1, *tmpx = DEN, *tmpy = DEN + 8 * U1;   // scratch (cleared below)
+    for (int i = lane; i < PER_WARP; i += 32) base[i] = 0.0;
+    const int b = (int)(item / A.nveh);
+    const int v = A.veh_begin + (int)(item - (long long)b * A.nveh);
+    const double *row = A.cpts + ((size_t)b * A.N + v) * A.S;
+    const double val = (double)m / __ldg(A.tf + b);              // diffMatrix(m, tf): m/tf
+    __syncwarp();
+
+    // pos.elev(E)   (bezier.py:469-495); the 2 (n+1) control points go through the (still unused) ring
+    // so that every lane reads them as shared-memory broadcasts instead of 2 (n+1) global loads per output
+    for (int j = lane; j < 2 * (n + 1); j += 32) Z[j] = __ldg(row + j);
+    __syncwarp();
+    for (int i = lane; i < m1; i += 32) {
+        double sx = 0.0, sy = 0.0;
+        for (int j = 0; j <= n; ++j) {
+            const double tt = __ldg(A.Tpos + (size_t)j * m1 + i);
+            sx = fma(Z[j], tt, sx);
+            sy = fma(Z[n + 1 + j], tt, sy);
+        }
+        px[i] = sx;
+        py[i] = sy;
+    }
+    __syncwarp();
+    for (int j = lane; j < 2 * (n + 1); j += 32) Z[j] = 0.0;       // the ring starts zeroed
+    __syncwarp();
+    // first derivatives: np.dot(cpts, Dm) then .elev(1)   (bezier.py:497-519)
+    for (int k = lane; k < m; k += 32) {
+        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
+        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
+    }
+    __syncwarp();
+    for (int k = lane; k < m1; k += 32) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        px[k] = qx;                                  // x', y' (unscaled) reuse px, py
+        py[k] = qy;
+    }
+    __syncwarp();
+    for (int k = lane; k < m; k += 32) {
+        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
+        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
+    }
+    __syncwarp();
+    for (int k = lane; k < m1; k += 32) {
+        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k), c = __ldg(A.Cm + k);
+        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
+        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
+        XDN[k] = -(qx * c);                          // pre-scaled by C(m,k); x'' stored negated
+        YDD[k] = qy * c;
+        XD[k] = px[k] * c;
+        YD[k] = py[k] * c;
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * ROW2; i += 32) (NUM - kMmaGuard)[i] = 0.0;        // scratch is dead: clear the rows
+    __syncwarp();
+
+    // ---- degree-2m curves, pre-scaled by C(2m,k) (optimization.py:603,605)
+    {
+        ConvRegs<U1> R1, R2;
+        conv_load<U1>(R1, YDD, XD, g, t);            // y'' * x'
+        conv_load<U1>(R2, XDN, YD, g, t);            // (-x'') * y'
+        conv_all<U1, false, true, (U1 % 2 == 1)>(R1, R2, Z, NUM, 1.0, g, t, lane);
+        conv_load<U1>(R1, XD, XD, g, t);             // x' * x'
+        conv_load<U1>(R2, YD, YD, g, t);             // y' * y'
+        conv_all<U1, true, true, (U1 % 2 == 1)>(R1, R2, Z, DEN, 2.0, g, t, lane);   // half squares: exact x 2
+    }
+    __syncwarp();
+    // ---- squares (optimization.py:604,606); both come out halved, which cancels in the ratio
+    {
+        ConvRegs<U2> R;
+        conv_load<U2>(R, NUM, NUM, g, t);
+        __syncwarp();
+        conv_all<U2, true, false, (U1 % 2 == 1)>(R, R, Z, N2, 1.0, g, t, lane);    // overwrites the degree-m rows
+        conv_load<U2>(R, DEN, DEN, g, t);
+        __syncwarp();                                                        // operands in registers: rows dead
+        conv_all<U2, true, false, (U1 % 2 == 1)>(R, R, Z, D2, 1.0, g, t, lane);
+    }
+    __syncwarp();
+    // ---- control-point-wise ratio (optimization.py:608)
+    double *out = A.out + (size_t)item * L4;
+    for (int k = lane; k < L4; k += 32) out[k] = fma(A.alpha, N2[k] / D2[k], A.beta);
+}
+
+template <int U1>
+static int launch_angrate_mma(const AngArgs &A, cudaStream_t st) {
+    constexpr int U2 = 2 * U1;
+    constexpr int ROW1 = kMmaGuard + 8 * U1 + kMmaGuard + 8, ROW2 = kMmaGuard + 8 * U2 + kMmaGuard + 8;
+    const size_t shw = sizeof(double) * (size_t)(4 * ROW1 + 2 * ROW2 + kRingDoubles) * kMmaWarps;
+    int sms_ = 0, per_sm_ = 0;
+    if (int rc = bez_kernel_config((const void *)angrate_mma_kernel<U1>, 32 * kMmaWarps, shw, &sms_, &per_sm_)) return rc;
+    const long long items = (long long)A.B * A.nveh;
+    angrate_mma_kernel<U1><<<(unsigned)((items + kMmaWarps - 1) / kMmaWarps), 32 * kMmaWarps, shw, st>>>(A);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
+}
+
 static WarpPlan2 make_warp_plan2(int m) {
     WarpPlan2 W;
     const int m1 = m + 1, L2 = 2 * m + 1;
@@ -662,7 +911,17 @@ extern "C" int bez_angrate_sq(const bez_angrate_tables *t, const double *d_cpts,
     A.n = t->n; A.m = t->m; A.veh_begin = veh_begin; A.nveh = nveh; A.alpha = alpha; A.beta = beta;
     // BEZGPU_ANGRATE_V1=1 forces the first-generation kernel (A/B runs, tools/check_angrate.py)
     const char *force_v1 = getenv("BEZGPU_ANGRATE_V1");
-    const char *gen = getenv("BEZGPU_ANGRATE_GEN");                   // "2": second generation (A/B runs)
+    const char *gen = getenv("BEZGPU_ANGRATE_GEN");                   // "2" / "3": earlier generations (A/B runs)
+    if (!(force_v1 && force_v1[0] == '1') && !(gen && (gen[0] == '2' || gen[0] == '3'))) {
+        // fourth generation (DMMA): instantiated for the block counts U1 = ceil((m+1)/8) in use
+        switch ((t->m + 1 + 7) / 8) {
+#define CASE(u_) case u_: return launch_angrate_mma<u_>(A, (cudaStream_t)stream);
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+            CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+            default: break;                                          // m > 127: first-generation kernel
+        }
+    }
     if (t->m <= 127 && !(force_v1 && force_v1[0] == '1') && !(gen && gen[0] == '2')) {
         const WarpPlan2 W = make_warp_plan2(t->m);                   // half-warp split, R = 8 / 16
         const size_t shw = sizeof(double) * (size_t)W.per_warp * kWarpsW;

@@ -116,13 +116,19 @@ struct MinSinks {
 
 // v = minimum of item (8 t + g) held by lane (g, t) = 4 g + t  ->  all sinks.  g0 = flattened
 // index of the tile's first item (a multiple of 32), cnt = live items of the tile.
+__device__ __forceinline__ void emit_minima_item_order(const MinSinks &S, double vi, long long g0, int cnt, int lane);
 __device__ __forceinline__ void emit_minima(const MinSinks &S, double v, long long g0, int cnt, int lane) {
     // to item order: lane l takes the minimum of item l (coalesced stores, ballot bit = item)
     const double vi = __shfl_sync(0xffffffffu, v, 4 * (lane & 7) + (lane >> 3));
+    emit_minima_item_order(S, vi, g0, cnt, lane);
+}
+
+// The same for a warp whose lane l already holds the minimum of item g0 + l (cnt <= 0: none live).
+__device__ __forceinline__ void emit_minima_item_order(const MinSinks &S, double vi, long long g0, int cnt, int lane) {
     const bool valid = lane < cnt;
     const long long f = g0 + lane;
     long long dst = f;
-    if (S.min_pitch > 0) {                              // rows of the destination are wider than this launch
+    if (S.min_pitch > 0) {
         const long long b = f / S.nitems;
         dst = b * S.min_pitch + (f - b * S.nitems);
     }
@@ -135,7 +141,7 @@ __device__ __forceinline__ void emit_minima(const MinSinks &S, double v, long lo
     if (S.mask || S.list_count) {                       // warp-uniform
         const bool act = valid && vi < S.threshold;
         const unsigned bal = __ballot_sync(0xffffffffu, act);
-        if (S.mask && lane == 0) S.mask[g0 >> 5] = bal;
+        if (S.mask && lane == 0 && cnt > 0) S.mask[g0 >> 5] = bal;
         if (S.list_count && bal) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(S.list_count, (unsigned long long)__popc(bal));
@@ -162,7 +168,7 @@ template <int N_, int NP, int MINMODE, bool STORE>
 __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
                                          const BFrags<N_, NP> &B, double *__restrict__ outg,
                                          const MinSinks &S, long long g0, int cnt,
-                                         int L, double beta, int lane, bool base_aligned, int dbg = 0) {
+                                         int L, double beta, int lane, bool base_aligned) {
     constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO;
     const int g = lane >> 2, t = lane & 3;
     const int M = L - 1;
@@ -251,16 +257,13 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
             mnv[mi] = m;
         }
         if (STORE) {
-            if (!(dbg & 8)) fence_async_smem();     // generic-proxy writes -> visible to the TMA read
+            fence_async_smem();                     // generic-proxy writes -> visible to the TMA read
             __syncwarp();
             const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
             double *dst = outg + (size_t)8 * mi * L;
             const unsigned bytes = (unsigned)(nrows * L) * 8u;
             if (base_aligned && (nrows == 8 || (bytes & 15u) == 0)) {
-                if (lane == 0) {
-                    if (!(dbg & 4)) bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes);
-                    bulk_commit();
-                }
+                if (lane == 0) { bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes); bulk_commit(); }
             } else {                                // odd row count x odd L or unaligned base
                 for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
                 if (lane == 0) bulk_commit();       // empty group keeps the count in step

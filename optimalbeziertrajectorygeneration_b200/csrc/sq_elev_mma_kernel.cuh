@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "sq_elev_stage1.cuh"
+#include "sq_elev_team.cuh"
 
 namespace bezmma_inst {
 using namespace bezcore;
@@ -37,7 +38,10 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
     const long long nwt = (total + 31) >> 5;
     const long long gwarp = (long long)blockIdx.x * kWarps + warp;
     const long long nwarps = (long long)gridDim.x * kWarps;
-    const bool strided = (A.flags & kFlagStridedTiles) != 0;
+    // contiguous runs pay off when an evaluation has many items (incremental decode); with few
+    // items per evaluation (C5: 16 pair rows) every tile needs a full decode anyway and the
+    // warp-strided order keeps all SMs writing one compact window of HBM (measured: 5 % faster)
+    const bool strided = (A.flags & kFlagStridedTiles) != 0 || MODE != PAIR || A.nitems < 4096;
     long long wt = strided ? gwarp : gwarp * nwt / nwarps;
     const long long wt_end = strided ? nwt : (gwarp + 1) * nwt / nwarps;
     const long long wt_step = strided ? nwarps : 1;
@@ -89,7 +93,7 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
         }
         __syncwarp();
         mma_tile<N_, NP, MINMODE, STORE>(rows, obuf, obuf_s, Bf, STORE ? A.out + (size_t)g0 * A.L : nullptr, A.sinks,
-                                         g0, cnt, A.L, A.beta, lane, base_aligned, A.flags);
+                                         g0, cnt, A.L, A.beta, lane, base_aligned);
         __syncwarp();
     }
     if (STORE && lane == 0) bulk_wait_all();      // staging buffers must outlive the last bulk reads
@@ -114,6 +118,11 @@ int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t s
     long long grid = (long long)sms * per_sm;
     const long long need = (nwt + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
+    // Fused all-gather: the caller's completion barrier (a tiny kernel on a high-priority side
+    // stream, sharding.PeerMinima) has to run *next to* the following persistent launch, so one
+    // CTA slot of the machine is left free for it (0.3 % of the grid) -- otherwise it only gets
+    // an SM when a whole persistent kernel has drained and ends up between two of them.
+    if (A.sinks.npeers > 0 && grid == (long long)sms * per_sm && grid > 1 && !(A.flags & kFlagFullGridWithPeers)) grid -= 1;
     if (grid < 1) return BEZ_OK;
     kern<<<(unsigned)grid, kThreads, shmem, st>>>(A, PW, DW);
     BEZ_CUDA(cudaGetLastError());
@@ -125,6 +134,13 @@ template <int N_, int DIM, int MODE, int NP>
 int mma_dispatch_variant(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     const bezmma::MinSinks &S = A.sinks;
     const bool wm = S.itemmin || S.mask || S.list_count || S.npeers > 0;
+    if constexpr (NP == 4) {
+        if (A.flags & kFlagTeam) {
+            if (A.out == nullptr) return bezteam::launch_sq_elev_team<N_, DIM, MODE, 1, false>(plan, A, st);
+            return wm ? bezteam::launch_sq_elev_team<N_, DIM, MODE, 1, true>(plan, A, st)
+                      : bezteam::launch_sq_elev_team<N_, DIM, MODE, 0, true>(plan, A, st);
+        }
+    }
     if (A.out == nullptr) {
         if (MODE == PAIR) return launch_sq_elev_mma<N_, DIM, MODE, NP, 1, false>(plan, A, st);
         bez_set_error("rows may only be skipped for the pair kernel");

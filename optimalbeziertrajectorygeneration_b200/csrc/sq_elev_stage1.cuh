@@ -25,8 +25,10 @@ struct SqElevArgs {
 };
 constexpr int kFlagPrefetchL1 = 1;     // prefetch.global.L1 of the next tile's vehicle rows
 constexpr int kFlagStridedTiles = 2;   // round-1 tile order (warp-strided, full decode per tile)
-constexpr int kFlagNoBulkStore = 4;    // ablation (wrong results): staging + fences, but no TMA store
-constexpr int kFlagNoFence = 8;        // ablation (unsafe): no fence.proxy.async before the TMA store
+// (bits 4 and 8 were the round-2 ablations "no TMA store" / "no fence": profiles/r02_ablation_pair_kernel.txt)
+constexpr int kFlagFullGridWithPeers = 16;   // A/B: do not leave a CTA slot free for the completion barrier
+constexpr int kFlagTeam = 32;          // 65 <= L <= 128: third-generation team kernel (sq_elev_team.cuh)
+
 
 // Position of a lane's item in the lexicographic pair list, advanced incrementally from tile
 // to tile (a warp owns a contiguous run of tiles): no 64-bit division, square root and fix-up

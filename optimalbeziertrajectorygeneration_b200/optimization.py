@@ -633,6 +633,15 @@ class BezOptimization:
                     ev.record(up)
                 return ev
 
+            def launch(ws, b, pa, va):
+                pa.reset()
+                cpts, tf = eng.assemble(ws['x'][:b], E)
+                eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b] if rows else None, rows=rows,
+                               pairmin=ws['pairmin'][:b], active=pa)
+                eng.speed(cpts, tf, E, -1.0, max_speed2, nveh=nv, out=ws['maxspeed'][:b], vehmin=ws['vehmin'][:b],
+                          active=va)
+
+            use_graph = bool(getattr(self, 'sweep_cuda_graphs', True))
             up.wait_stream(main)
             x_ready = upload(0, None)
             prev_ready = None
@@ -648,14 +657,21 @@ class BezOptimization:
                 if b != chunk:                          # ragged last chunk: its own, smaller destinations
                     pa = _engine.ActiveSet(b * P, cap, eng.device, threshold)
                     va = _engine.ActiveSet(b * nv, 0, eng.device, 0.0)
+                    launch(ws, b, pa, va)
                 else:
                     pa, va = ws['pairs'], ws['vehs']
-                    pa.reset()
-                cpts, tf = eng.assemble(ws['x'][:b], E)
-                eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b] if rows else None, rows=rows,
-                               pairmin=ws['pairmin'][:b], active=pa)
-                eng.speed(cpts, tf, E, -1.0, max_speed2, nveh=nv, out=ws['maxspeed'][:b], vehmin=ws['vehmin'][:b],
-                          active=va)
+                    if ws.get('graph') is None and use_graph:
+                        # the fixed launch sequence of a full chunk (counter reset, assemble, fused
+                        # pair kernel, speed kernel) replays as one CUDA graph: no launch gaps
+                        launch(ws, b, pa, va)                   # warm-up: plans, kernel attributes
+                        main.synchronize()
+                        ws['graph'] = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(ws['graph']):
+                            launch(ws, b, pa, va)
+                    if ws.get('graph') is not None:
+                        ws['graph'].replay()
+                    else:
+                        launch(ws, b, pa, va)
                 ready = torch.cuda.Event()
                 ready.record(main)
                 prev_ready = ready

@@ -55,7 +55,22 @@ for flags in os.environ.get("AB_FLAGS", "0,2,1").split(","):
         ms = timeit(fn)
         print("flags=%s %-20s mean %.4f ms  min %.4f ms  -> %.0f GB/s = %.3f of 6484.6" %
               (flags, name, ms.mean(), ms.min(), gb / (ms.mean() * 1e-3), gb / (ms.mean() * 1e-3) / 6484.6), flush=True)
-ref = out.min(dim=2).values
 os.environ["BEZGPU_MMA_FLAGS"] = "0"
 eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm)
 print("min == row min:", bool(torch.equal(pm, out.min(dim=2).values)), " active pairs:", int((pm < 0).sum()))
+# every flag set must reproduce the flags=0 bits (values, minima, mask, list)
+ref_out, ref_pm = out[:1].clone(), pm.clone()
+for flags in os.environ.get("AB_FLAGS", "0,2,1").split(","):
+    if int(flags) & 12:
+        continue                                    # ablations: wrong by construction
+    os.environ["BEZGPU_MMA_FLAGS"] = flags
+    out.fill_(float("nan")); pm.fill_(float("nan")); act.reset()
+    eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm, active=act)
+    torch.cuda.synchronize()
+    fl, idx, val, over = ActiveSet.decode(act.buf.cpu().numpy(), B * P, act.capacity)
+    pmh = ref_pm.cpu().numpy().ravel()
+    ok = (torch.equal(out[:1], ref_out) and torch.equal(pm, ref_pm) and torch.equal(out.min(dim=2).values, ref_pm)
+          and np.array_equal(fl, pmh < 0) and np.array_equal(val, pmh[pmh < 0]) and not over)
+    pm2 = torch.full_like(pm, float("nan"))
+    eng.separation(cpts, E, args["maxSep"], pairmin=pm2, rows=False)
+    print("flags=%s bit-identical to flags=0: %s   minima-only identical: %s" % (flags, ok, bool(torch.equal(pm2, ref_pm))))
