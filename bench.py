@@ -324,8 +324,9 @@ def run_ours(opts):
     if world > 1 and not opts.nccl_gather:
         try:
             peer = sharding.PeerMinima(B, P, eng.device, layout="pairs" if strong else "batch")
-            gather_mode = ("fused: in-kernel NVLink peer stores into symmetric memory; signal-pad barrier on a "
-                           "high-priority side stream, three rotating matrices")
+            gather_mode = ("fused: in-kernel NVLink %s into symmetric memory; signal-pad barrier on a "
+                           "high-priority side stream, three rotating matrices"
+                           % ("multicast stores (NVSwitch replicates to every rank)" if peer.mc_ptr else "peer stores"))
         except Exception as e:                      # symmetric memory not available on this box
             if rank == 0:
                 print("PeerMinima unavailable (%r); falling back to NCCL all-gather" % (e,), file=sys.stderr)
@@ -809,7 +810,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="evals (x vectors) per step per GPU")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="evals (x vectors) per step: per GPU with --scaling weak (default 4), in total with "
+                         "--scaling strong (default 32 = the work of 8 weak-scaling ranks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--clock-period", type=float, default=0.002, help="NVML sampling period in seconds")
     ap.add_argument("--nccl-gather", action="store_true",
@@ -826,6 +829,8 @@ def main():
     ap.add_argument("--slsqp-full", action="store_true",
                     help="run every SLSQP arm of C3 to convergence (the host arm takes minutes)")
     opts = ap.parse_args()
+    if opts.batch <= 0:
+        opts.batch = 32 if opts.scaling == "strong" else 4
     if opts.impl == "reference":
         run_reference(opts)
     elif opts.workload == "c5":

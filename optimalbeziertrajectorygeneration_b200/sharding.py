@@ -168,6 +168,18 @@ class PeerMinima:
         self.buf = symm_mem.empty((self.NBUF, rows, self.P), dtype=torch.float64, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        # NVSwitch multicast (NVLS): one store to the multicast address of the symmetric buffer lands
+        # in every rank's copy (this rank's included), replicated inside the switch -- one remote store
+        # per tile instead of world-1, and 1x instead of (world-1)x NVLink egress.  multimem.st of an
+        # f64 is a plain STG to that address, so the kernel needs no separate code path: the multicast
+        # address is handed over as the only "peer".  BEZGPU_PEER_MULTICAST=0 keeps the per-peer stores.
+        import os
+        self.mc_ptr = 0
+        try:
+            if os.environ.get("BEZGPU_PEER_MULTICAST", "1") != "0" and self.world > 1:
+                self.mc_ptr = int(self.hdl.multicast_ptr or 0)
+        except Exception:
+            self.mc_ptr = 0
         self.side = torch.cuda.Stream(device=device, priority=-1)
         self.done = [None] * self.NBUF
         self.k = 0
@@ -185,7 +197,10 @@ class PeerMinima:
         else:
             off = (i * self.rows * self.P + self.pair_lo) * 8
             local = self.buf[i, :, self.pair_lo:]
-        peers = [self.ptrs[r] + off for r in range(self.world) if r != self.rank]
+        if self.mc_ptr:
+            peers = [self.mc_ptr + off]
+        else:
+            peers = [self.ptrs[r] + off for r in range(self.world) if r != self.rank]
         return local, peers
 
     def complete(self):
