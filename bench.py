@@ -687,6 +687,19 @@ def slsqp_measure(full=False):
     Jt = b.temporalSeparationConstraints_jac(x0)
     c3["jacobian_ms_gpu"] = 1e3 * (time.perf_counter() - t0)
     c3["jacobian_shape"] = list(Jt.shape)
+    # the latency-bound regime: one closure call = H2D of x, assemble, pair kernel (630 x 11 values), D2H, sync
+    f = b.temporalSeparationConstraints
+    f(x0)
+    t0 = time.perf_counter()
+    for _ in range(433):
+        f(x0)
+    dt = time.perf_counter() - t0
+    c3["closure_calls_per_s"] = 433 / dt
+    c3["fd_jacobian_by_433_calls_ms"] = 1e3 * dt
+    t0 = time.perf_counter()
+    for _ in range(20):
+        hsep(x0)
+    c3["host_closure_calls_per_s"] = 20 / (time.perf_counter() - t0)
     c3["problem"] = ("SwarmOfAerialVehicles: 36 vehicles, 3-D, degree 5, nvar 432, DEG_ELEV 0, 630 pairs x 11 values; "
                      "objective at x0 = 382.0101330471013")
     out["c3"] = c3
