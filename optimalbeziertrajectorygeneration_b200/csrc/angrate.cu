@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(32 * kMmaWarps, 4) angrate_mma_kernel(const An
     double *Z = base + 4 * ROW1 + 2 * ROW2;                       // [32][8] ring
     double *N2 = base;                                            // NUM^2 (16 U2 doubles) over the dead degree-m rows
     double *D2 = base + 4 * ROW1;                                 // DEN^2 over the dead NUM | DEN rows
-    double *px = NUM, *py = NUM + 8 * U1, *tmpx = DEN, *tmpy = DEN + 8 * U1;   // scratch (cleared below)
+    double *px = NUM, *py = NUM + 8 * U1;                         // scratch (cleared below)
     for (int i = lane; i < PER_WARP; i += 32) base[i] = 0.0;
     const int b = (int)(item / A.nveh);
     const int v = A.veh_begin + (int)(item - (long long)b * A.nveh);
@@ -725,33 +725,56 @@ __global__ void __launch_bounds__(32 * kMmaWarps, 4) angrate_mma_kernel(const An
     __syncwarp();
     for (int j = lane; j < 2 * (n + 1); j += 32) Z[j] = 0.0;       // the ring starts zeroed
     __syncwarp();
-    // first derivatives: np.dot(cpts, Dm) then .elev(1)   (bezier.py:497-519)
-    for (int k = lane; k < m; k += 32) {
-        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
-        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
-    }
-    __syncwarp();
+    // first and second derivatives in one pass: Bezier.diff = np.dot(cpts, Dm) then .elev(1)
+    // (bezier.py:497-519), twice.  Output k needs x'_{k-1..k+1}, i.e. the position control points
+    // k-2 .. k+2: every lane recomputes that 5-point stencil in registers with exactly the operation
+    // order of the separate passes (same bits), instead of four passes through shared memory with a
+    // warp barrier each.
     for (int k = lane; k < m1; k += 32) {
-        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k);
-        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
-        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
-        px[k] = qx;                                  // x', y' (unscaled) reuse px, py
-        py[k] = qy;
-    }
-    __syncwarp();
-    for (int k = lane; k < m; k += 32) {
-        tmpx[k] = px[k] * (-val) + px[k + 1] * val;
-        tmpy[k] = py[k] * (-val) + py[k + 1] * val;
-    }
-    __syncwarp();
-    for (int k = lane; k < m1; k += 32) {
-        const double lo = __ldg(A.lo + k), hi = __ldg(A.hi + k), c = __ldg(A.Cm + k);
-        double qx = (k < m) ? tmpx[k] * lo : 0.0, qy = (k < m) ? tmpy[k] * lo : 0.0;
-        if (k > 0) { qx = tmpx[k - 1] * hi + qx; qy = tmpy[k - 1] * hi + qy; }
-        XDN[k] = -(qx * c);                          // pre-scaled by C(m,k); x'' stored negated
-        YDD[k] = qy * c;
-        XD[k] = px[k] * c;
-        YD[k] = py[k] * c;
+        double P[2][5];
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+            const int j = k - 2 + o;
+            const bool in = j >= 0 && j <= m;
+            P[0][o] = in ? px[j] : 0.0;
+            P[1][o] = in ? py[j] : 0.0;
+        }
+        double lo[3], hi[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const int j = k - 1 + o;
+            const bool in = j >= 0 && j <= m;
+            lo[o] = in ? __ldg(A.lo + j) : 0.0;
+            hi[o] = in ? __ldg(A.hi + j) : 0.0;
+        }
+        const double c = __ldg(A.Cm + k);
+        double d1[2], d2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double T[4], D[3];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {            // tmp_j = p_j (-val) + p_{j+1} val,  j = k-2+o, valid for 0 <= j < m
+                const int j = k - 2 + o;
+                T[o] = (j >= 0 && j < m) ? P[q][o] * (-val) + P[q][o + 1] * val : 0.0;
+            }
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {            // x'_j, j = k-1+o: tmp_j lo_j (j < m) then + tmp_{j-1} hi_j (j > 0)
+                const int j = k - 1 + o;
+                double qv = (j >= 0 && j < m) ? T[o + 1] * lo[o] : 0.0;
+                if (j > 0 && j <= m) qv = T[o] * hi[o] + qv;
+                D[o] = qv;
+            }
+            d1[q] = D[1];
+            const double t0 = (k - 1 >= 0 && k - 1 < m) ? D[0] * (-val) + D[1] * val : 0.0;     // tmp2_{k-1}
+            const double t1 = (k < m) ? D[1] * (-val) + D[2] * val : 0.0;                         // tmp2_k
+            double qv = (k < m) ? t1 * lo[1] : 0.0;
+            if (k > 0) qv = t0 * hi[1] + qv;
+            d2[q] = qv;
+        }
+        XDN[k] = -(d2[0] * c);                       // pre-scaled by C(m,k); x'' stored negated
+        YDD[k] = d2[1] * c;
+        XD[k] = d1[0] * c;
+        YD[k] = d1[1] * c;
     }
     __syncwarp();
     for (int i = lane; i < 2 * ROW2; i += 32) (NUM - kMmaGuard)[i] = 0.0;        // scratch is dead: clear the rows
@@ -781,7 +804,19 @@ __global__ void __launch_bounds__(32 * kMmaWarps, 4) angrate_mma_kernel(const An
     __syncwarp();
     // ---- control-point-wise ratio (optimization.py:608)
     double *out = A.out + (size_t)item * L4;
-    for (int k = lane; k < L4; k += 32) out[k] = fma(A.alpha, N2[k] / D2[k], A.beta);
+    // N2 / D2 with a branch-free division: rcp.approx (2^-23) + two Newton steps + one residual
+    // correction of the quotient (the operands are far from the overflow / subnormal ranges that
+    // the generic DDIV sequence guards against: |D2| ~ C(2m,.)^4 v^4 stays below 1e260 for m <= 127)
+    for (int k = lane; k < L4; k += 32) {
+        const double nn = N2[k], dd = D2[k];
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dd));
+        r = fma(fma(-dd, r, 1.0), r, r);
+        r = fma(fma(-dd, r, 1.0), r, r);
+        double q = nn * r;
+        q = fma(fma(-dd, q, nn), r, q);
+        out[k] = fma(A.alpha, q, A.beta);
+    }
 }
 
 template <int U1>

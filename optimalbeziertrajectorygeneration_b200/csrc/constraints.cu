@@ -266,6 +266,30 @@ __global__ void emit_from_minima_kernel(bezmma::MinSinks S, long long total) {
     }
 }
 
+// Compacted (f, min) list from the packed bitmask + the minimum matrix: one thread per mask word,
+// one atomic per non-empty word.  Large launches of the tensor-path kernels use this instead of
+// appending from the epilogue: the append costs the hot kernel 2 % (an atomic round trip in front
+// of a warp-wide shuffle for every tile that has an active item), this pass ~3 us.
+__global__ void compact_from_mask_kernel(bezmma::MinSinks S, long long total) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= ((total + 31) >> 5)) return;
+    unsigned bits = S.mask[w];
+    if (!bits) return;
+    long long pos = (long long)atomicAdd(S.list_count, (unsigned long long)__popc(bits));
+    while (bits) {
+        const int bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const long long f = (w << 5) + bit;
+        long long src = f;
+        if (S.min_pitch > 0) {
+            const long long b = f / S.nitems;
+            src = b * S.min_pitch + (f - b * S.nitems);
+        }
+        if (pos < S.list_cap) { S.list_idx[pos] = f; S.list_val[pos] = S.itemmin[src]; }
+        ++pos;
+    }
+}
+
 static int fill_sinks(bezmma::MinSinks &S, const bez_reduce_opts *o, long long nitems, double *legacy_min) {
     memset(&S, 0, sizeof(S));
     S.nitems = nitems;
@@ -295,8 +319,20 @@ static int run_sq_elev(const bez_plan *plan, SqElevArgs &A, int mode, const bez_
     const bool derived = S.mask || S.list_count;
     BEZ_REQUIRE(A.out || S.itemmin || derived || S.npeers > 0, "nothing to compute: no rows and no minima requested");
     A.flags = bez_sq_elev_mma_flags();
-    if (bez_sq_elev_mma_supported(plan) && (A.out || mode == PAIR))
-        return bez_sq_elev_mma(plan, A, mode, st);
+    if (bez_sq_elev_mma_supported(plan) && (A.out || mode == PAIR)) {
+        const long long total = A.nitems * (long long)A.B;
+        const bool defer_list = S.list_count && S.mask && S.itemmin && total >= (1 << 16) &&
+                                !(A.flags & kFlagFusedList);
+        unsigned long long *list_count = A.sinks.list_count;
+        if (defer_list) A.sinks.list_count = nullptr;          // the kernel still packs the bitmask
+        int rc = bez_sq_elev_mma(plan, A, mode, st);
+        A.sinks.list_count = list_count;
+        if (rc != BEZ_OK || !defer_list) return rc;
+        const long long words = (total + 31) >> 5;
+        compact_from_mask_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(A.sinks, total);
+        BEZ_CUDA(cudaGetLastError());
+        return BEZ_OK;
+    }
     // column-stationary DFMA kernels: rows are always written; minima to the local matrix only
     if (!A.out || S.npeers > 0) {
         bez_set_error("degree %d / elevation %d / dim %d is outside the tensor-path kernels: rows cannot be "

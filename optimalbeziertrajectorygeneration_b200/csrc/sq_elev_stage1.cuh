@@ -27,6 +27,7 @@ constexpr int kFlagPrefetchL1 = 1;     // prefetch.global.L1 of the next tile's 
 constexpr int kFlagStridedTiles = 2;   // round-1 tile order (warp-strided, full decode per tile)
 // (bits 4 and 8 were the round-2 ablations "no TMA store" / "no fence": profiles/r02_ablation_pair_kernel.txt)
 constexpr int kFlagFullGridWithPeers = 16;   // A/B: do not leave a CTA slot free for the completion barrier
+constexpr int kFlagFusedList = 64;     // A/B: append the active list from the epilogue even in large launches
 constexpr int kFlagTeam = 32;          // 65 <= L <= 128: third-generation team kernel (sq_elev_team.cuh)
 
 

@@ -23,6 +23,20 @@ from . import engine as _engine
 DEG_ELEV = 0
 
 
+def _on_model_device(method):
+    """Runs a method with the model's device current (a model built with ``device=k`` works
+    whatever device the calling thread has selected; the caller's device is restored)."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *a, **k):
+        if self._device is None or not torch.cuda.is_available() or torch.cuda.current_device() == self._device:
+            return method(self, *a, **k)
+        with torch.cuda.device(self._device):
+            return method(self, *a, **k)
+    return wrapper
+
+
 def _deg_elev():
     # re-read the module global at call time, like the reference (Q9)
     return int(globals()['DEG_ELEV'])
@@ -280,6 +294,7 @@ class BezOptimization:
         self._spatial_check(status[0])
         return rows[0] - self.model['maxSep']
 
+    @_on_model_device
     def spatialSeparationConstraints_jac(self, x):
         """Additive: the '2-point' FD Jacobian SLSQP would form from nvar+1 calls of
         spatialSeparationConstraints, [npairs*3, nvar]: the base point and all perturbed
@@ -411,6 +426,7 @@ class BezOptimization:
             rows.append([tf])
         return np.concatenate(rows)
 
+    @_on_model_device
     def reshapeVector(self, x):
         """optimization.py:242-285, evaluated by the device assemble kernel
         (the same one every constraint closure uses) and copied back as the
@@ -423,6 +439,7 @@ class BezOptimization:
 
     # ------------------------------------------------------------------
     # additive, batched API
+    @_on_model_device
     def evaluate_batch(self, X, which=('sep', 'maxspeed'), elev=None):
         """Evaluates the named constraint blocks for every row of X [B, nvar]
         in one pass; returns device tensors {name: [B, m_name]}."""
@@ -445,6 +462,7 @@ class BezOptimization:
                                             ).reshape(d_x.shape[0], -1)
         return res
 
+    @_on_model_device
     def evaluate_reduced(self, X, elev=None):
         """Additive API for swarms whose full constraint vector is consumed on the
         device (508 MB per x at N=1024): host X [B, nvar] -> host arrays
@@ -481,6 +499,7 @@ class BezOptimization:
             pmh, sph = pmh.copy(), sph.copy()
         return {'pairmin': pmh, 'maxspeed': sph}
 
+    @_on_model_device
     def evaluate_sweep(self, X, elev=None, chunk=4, out=None):
         """Pipelined form of :meth:`evaluate_reduced` for the nvar+1 points of a finite
         difference sweep (SciPy asks for them one by one, `_numdiff.py:683-712`; here the
@@ -571,6 +590,7 @@ class BezOptimization:
         self.workspace = {'key': None, 'sep': sw['sets'][(k & 1)]['sep']}
         return {'pairmin': out['pairmin'].numpy(), 'maxspeed': out['maxspeed'].numpy()}
 
+    @_on_model_device
     def evaluate_sweep_active(self, X, elev=None, chunk=4, threshold=0.0, rows=True):
         """Like :meth:`evaluate_sweep`, but only the *reduced* result of every evaluation leaves
         the device: the packed active bitmask of all pairs (1 bit per pair: min over the pair's
@@ -703,6 +723,7 @@ class BezOptimization:
         return res
 
     # -- cost callables (A14, optimization.py:287-308) -----------------------
+    @_on_model_device
     def _objective(self, x, kind):
         """One launch for every row of x: a 1-D x gives a float (the reference's
         callable), a 2-D batch [B, nvar] gives float64[B]."""
@@ -724,6 +745,7 @@ class BezOptimization:
         host = eng.download(out, key="out:objective")
         return float(host[0]) if single else host
 
+    @_on_model_device
     def _objective_grad(self, x, kind):
         """SciPy's '2-point' gradient of the objective (what SLSQP forms with nvar+1 calls,
         _slsqp_py.py:424-426) in one launch, cancellation free (bez_objective_grad)."""

@@ -94,3 +94,30 @@ def test_fused_allgather_matches_nccl():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(r[1] for r in res)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_engine_on_a_non_current_device():
+    """BezOptimization(device=1) while device 0 is current: the per-device kernel
+    attributes, the launch stream and the allocations must all follow the engine's device, and
+    the caller's current device must be left alone."""
+    from oracle.make_golden import synthetic_swarm_args
+    from optimalbeziertrajectorygeneration_b200 import optimization as gopt
+    torch.cuda.set_device(0)
+    args, x = synthetic_swarm_args(20)
+    gopt.DEG_ELEV = 100
+    try:
+        b0 = gopt.BezOptimization(**args, device=0)
+        b1 = gopt.BezOptimization(**args, device=1)
+        want = b0.temporalSeparationConstraints(x)          # ~96 KB dynamic shared memory: opt-in on device 0
+        got = b1.temporalSeparationConstraints(x)           # ... must also be granted on device 1
+        assert torch.cuda.current_device() == 0
+        assert np.array_equal(got, want)
+        assert np.array_equal(b1.maxSpeedConstraints(x), b0.maxSpeedConstraints(x))
+        assert np.array_equal(b1.temporalSeparationConstraints_jac(x), b0.temporalSeparationConstraints_jac(x))
+        red = b1.evaluate_sweep_active(np.stack([x, x + 0.01]), elev=100, chunk=2)
+        flags, _, _, _ = red.pairs(0)
+        assert flags.shape == (2, 190)
+        assert b1._engine(True).device.index == 1 and torch.cuda.current_device() == 0
+    finally:
+        gopt.DEG_ELEV = 0

@@ -373,3 +373,32 @@ def test_evaluate_sweep_active_matches_minima(gopt):
             import torch
             assert torch.equal(b.workspace['sep'][:3].min(dim=2).values.cpu(), torch.as_tensor(pm[8:11]))
     assert (pm < 5000.0).mean() > 0.05                       # the overflow path really ran
+
+
+def test_active_list_post_pass_equals_fused_append(gopt, monkeypatch):
+    """Large launches (>= 65536 items) build the compacted list in a post-pass from the bitmask
+    (the epilogue only packs the mask); BEZGPU_MMA_FLAGS=64 forces the fused append.  Both must
+    give the same set of (index, minimum) entries."""
+    import torch
+    from optimalbeziertrajectorygeneration_b200.engine import ActiveSet
+    from oracle.make_golden import synthetic_swarm_args
+    args, x = synthetic_swarm_args(200)
+    b = gopt.BezOptimization(**args)
+    eng = b._engine(True)
+    B, P = 4, 200 * 199 // 2
+    X = x[None, :] + np.random.default_rng(2).normal(size=(B, x.size)) * 0.1
+    cpts, _ = eng.assemble(eng.upload(X), 100)
+    pm = torch.empty((B, P), dtype=torch.float64, device=eng.device)
+    got = {}
+    for flags in ("0", "64"):
+        monkeypatch.setenv("BEZGPU_MMA_FLAGS", flags)
+        act = ActiveSet(B * P, capacity=B * P, device=eng.device, threshold=400.0)
+        eng.separation(cpts, 100, 0.9, pairmin=pm, active=act, rows=False)
+        torch.cuda.synchronize()
+        got[flags] = ActiveSet.decode(act.buf.cpu().numpy(), B * P, B * P)
+    ref = pm.cpu().numpy().ravel()
+    for flags in got:
+        fl, idx, val, over = got[flags]
+        assert not over and np.array_equal(fl, ref < 400.0)
+        assert np.array_equal(idx, np.nonzero(ref < 400.0)[0]) and np.array_equal(val, ref[ref < 400.0])
+    assert 100 < (ref < 400.0).sum() < B * P
