@@ -42,8 +42,9 @@ extern "C" {
 
 /* Degree limits (one place; INTEGRATION.md section 4 quotes these):
  *   plans and the fused constraint / objective kernels   n <= BEZ_MAX_DEGREE      = 16
- *   the fp64 tensor-path variants of those kernels        n <= BEZ_MAX_DEGREE_MMA  = 15, L <= 128, dim >= 2
- *                                                         (other shapes run the DFMA kernels)
+ *   the fp64 tensor-path variants of those kernels        n <= BEZ_MAX_DEGREE_MMA  = 15, dim >= 2 (TMA-store
+ *                                                         variant for L <= 128, column-tiled variant above;
+ *                                                         other shapes run the DFMA kernels)
  *   closed-form Jacobian kernels                          n <= BEZ_MAX_DEGREE_JAC  = 12
  *   angular rate                                          n + elev <= 250 (tensor path <= 127) */
 #define BEZ_MAX_DEGREE      16

@@ -266,16 +266,34 @@ __global__ void emit_from_minima_kernel(bezmma::MinSinks S, long long total) {
     }
 }
 
-// Compacted (f, min) list from the packed bitmask + the minimum matrix: one thread per mask word,
-// one atomic per non-empty word.  Large launches of the tensor-path kernels use this instead of
+// Compacted (f, min) list from the packed bitmask + the minimum matrix.  Large launches of the tensor-path kernels use this instead of
 // appending from the epilogue: the append costs the hot kernel 2 % (an atomic round trip in front
 // of a warp-wide shuffle for every tile that has an active item), this pass ~3 us.
 __global__ void compact_from_mask_kernel(bezmma::MinSinks S, long long total) {
+    // one thread per mask word, ONE atomic per block (256 words): block-wide exclusive scan of the
+    // per-word popcounts (same-address atomics serialise in L2: one per word cost more than the
+    // fused append it replaces)
+    __shared__ unsigned warp_sum[8];
+    __shared__ unsigned long long block_base;
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= ((total + 31) >> 5)) return;
-    unsigned bits = S.mask[w];
-    if (!bits) return;
-    long long pos = (long long)atomicAdd(S.list_count, (unsigned long long)__popc(bits));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned bits = (w < ((total + 31) >> 5)) ? S.mask[w] : 0u;
+    const unsigned cnt = __popc(bits);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { const unsigned v = warp_sum[i]; warp_sum[i] = tot; tot += v; }
+        block_base = tot ? atomicAdd(S.list_count, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    long long pos = (long long)block_base + warp_sum[warp] + (incl - cnt);
     while (bits) {
         const int bit = __ffs(bits) - 1;
         bits &= bits - 1;
@@ -319,7 +337,8 @@ static int run_sq_elev(const bez_plan *plan, SqElevArgs &A, int mode, const bez_
     const bool derived = S.mask || S.list_count;
     BEZ_REQUIRE(A.out || S.itemmin || derived || S.npeers > 0, "nothing to compute: no rows and no minima requested");
     A.flags = bez_sq_elev_mma_flags();
-    if (bez_sq_elev_mma_supported(plan) && (A.out || mode == PAIR)) {
+    if ((bez_sq_elev_mma_supported(plan) && (A.out || mode == PAIR)) ||
+        (bez_sq_elev_mma_wide_supported(plan) && A.out)) {
         const long long total = A.nitems * (long long)A.B;
         const bool defer_list = S.list_count && S.mask && S.itemmin && total >= (1 << 16) &&
                                 !(A.flags & kFlagFusedList);

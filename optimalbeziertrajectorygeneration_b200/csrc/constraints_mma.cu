@@ -33,6 +33,14 @@ bool bez_sq_elev_mma_supported(const bez_plan *plan) {
     return plan->n <= 15 && plan->Lh <= 64 && plan->dim >= 2 && !bez_force_dfma();
 }
 
+// L > 128: the column-tiled tensor-path variant (sq_elev_mma_wide.cuh); it always writes the rows
+bool bez_sq_elev_mma_wide_supported(const bez_plan *plan) {
+#ifdef BEZ_ONLY_N
+    if (plan->n != BEZ_ONLY_N) return false;
+#endif
+    return plan->n <= 15 && plan->Lh > 64 && plan->dim >= 2 && !bez_force_dfma();
+}
+
 int bez_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, int mode, cudaStream_t st) {
     const int n = plan->n;
     if (mode == PAIR) {

@@ -7,6 +7,7 @@
 
 #include "sq_elev_stage1.cuh"
 #include "sq_elev_team.cuh"
+#include "sq_elev_mma_wide.cuh"
 
 namespace bezmma_inst {
 using namespace bezcore;
@@ -152,6 +153,13 @@ int mma_dispatch_variant(const bez_plan *plan, const SqElevArgs &A, cudaStream_t
 
 template <int N_, int DIM, int MODE>
 int mma_dispatch_shape(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
+    if (plan->Lh > 64) {                                  // L > 128: column-tiled variant (rows always written)
+        if (A.out == nullptr) {
+            bez_set_error("L = %d > 128: the rows cannot be skipped", plan->L);
+            return BEZ_EUNSUPPORTED;
+        }
+        return bezwide::launch_sq_elev_mma_wide<N_, DIM, MODE, 1>(plan, A, st);
+    }
     if (plan->Lh <= 16) return mma_dispatch_variant<N_, DIM, MODE, 1>(plan, A, st);
     if (plan->Lh <= 32) return mma_dispatch_variant<N_, DIM, MODE, 2>(plan, A, st);
     return mma_dispatch_variant<N_, DIM, MODE, 4>(plan, A, st);

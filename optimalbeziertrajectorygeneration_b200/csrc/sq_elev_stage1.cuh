@@ -122,6 +122,7 @@ __device__ __forceinline__ void stage1_coeffs(const SqElevArgs &A, const ProdWei
 
 // constraints_mma.cu: fp64 tensor path for L <= 128, degree <= 15, dim 2 / 3
 bool bez_sq_elev_mma_supported(const bez_plan *plan);
+bool bez_sq_elev_mma_wide_supported(const bez_plan *plan);
 int bez_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, int mode, cudaStream_t st);
 int bez_sq_elev_mma_flags();
 

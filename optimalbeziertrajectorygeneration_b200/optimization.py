@@ -662,6 +662,13 @@ class BezOptimization:
                           active=va)
 
             use_graph = bool(getattr(self, 'sweep_cuda_graphs', True))
+            # Consecutive chunks run on two alternating compute streams (their workspaces are
+            # disjoint): the next chunk's kernels are already queued when the persistent pair kernel
+            # of the current one drains, so its CTAs fill the SMs as they free up -- no launch gap and
+            # no idle tail between chunks.
+            lanes = sw.setdefault('compute_streams', [torch.cuda.Stream(device=eng.device) for _ in range(2)])
+            for st in lanes:
+                st.wait_stream(main)
             up.wait_stream(main)
             x_ready = upload(0, None)
             prev_ready = None
@@ -669,31 +676,33 @@ class BezOptimization:
                 hi = min(M, lo + chunk)
                 b = hi - lo
                 ws = sw['sets'][k & 1]
-                if ws['done'] is not None:
-                    main.wait_event(ws['done'])
-                main.wait_event(x_ready)
-                if k + 1 < nchunks:
-                    x_ready = upload(k + 1, prev_ready)
-                if b != chunk:                          # ragged last chunk: its own, smaller destinations
-                    pa = _engine.ActiveSet(b * P, cap, eng.device, threshold)
-                    va = _engine.ActiveSet(b * nv, 0, eng.device, 0.0)
-                    launch(ws, b, pa, va)
-                else:
-                    pa, va = ws['pairs'], ws['vehs']
-                    if ws.get('graph') is None and use_graph:
-                        # the fixed launch sequence of a full chunk (counter reset, assemble, fused
-                        # pair kernel, speed kernel) replays as one CUDA graph: no launch gaps
-                        launch(ws, b, pa, va)                   # warm-up: plans, kernel attributes
-                        main.synchronize()
-                        ws['graph'] = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(ws['graph']):
-                            launch(ws, b, pa, va)
-                    if ws.get('graph') is not None:
-                        ws['graph'].replay()
-                    else:
+                st = lanes[k & 1]
+                with torch.cuda.stream(st):
+                    if ws['done'] is not None:
+                        st.wait_event(ws['done'])
+                    st.wait_event(x_ready)
+                    if k + 1 < nchunks:
+                        x_ready = upload(k + 1, prev_ready)
+                    if b != chunk:                          # ragged last chunk: its own, smaller destinations
+                        pa = _engine.ActiveSet(b * P, cap, eng.device, threshold)
+                        va = _engine.ActiveSet(b * nv, 0, eng.device, 0.0)
                         launch(ws, b, pa, va)
-                ready = torch.cuda.Event()
-                ready.record(main)
+                    else:
+                        pa, va = ws['pairs'], ws['vehs']
+                        if ws.get('graph') is None and use_graph:
+                            # the fixed launch sequence of a full chunk (counter reset, assemble, fused
+                            # pair kernel, speed kernel) replays as one CUDA graph: no launch gaps
+                            launch(ws, b, pa, va)                   # warm-up: plans, kernel attributes
+                            st.synchronize()
+                            ws['graph'] = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(ws['graph']):
+                                launch(ws, b, pa, va)
+                        if ws.get('graph') is not None:
+                            ws['graph'].replay()
+                        else:
+                            launch(ws, b, pa, va)
+                    ready = torch.cuda.Event()
+                    ready.record(st)
                 prev_ready = ready
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
@@ -702,6 +711,8 @@ class BezOptimization:
                     out_vmin[lo:hi].copy_(ws['vehmin'][:b], non_blocking=True)
                     ws['done'] = torch.cuda.Event()
                     ws['done'].record(side)
+            for st in lanes:
+                main.wait_stream(st)
             side.synchronize()
             main.synchronize()
             res = SweepActive(out_pairs.numpy(), out_vehs.numpy(), out_vmin.numpy(), M, chunk, P, nv, cap)

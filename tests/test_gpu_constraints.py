@@ -130,11 +130,12 @@ def test_batched_and_pair_ranges(gopt):
 @pytest.mark.parametrize("deg,E", [(10, 100),                       # C4 / C5: L = 121 (4 n-tile pairs)
                                    (5, 0), (5, 10), (5, 100),      # C3 swarm: L = 11 / 21 / 111
                                    (10, 0), (10, 30),              # C2 Example1: L = 21 / 51
-                                   (3, 10), (7, 0), (2, 0), (15, 33), (12, 103)])
+                                   (3, 10), (7, 0), (2, 0), (15, 33), (12, 103),
+                                   (10, 300), (5, 150), (12, 106), (4, 121)])   # L > 128: column-tiled variant
 def test_tensor_path_matches_dfma_path(gopt, monkeypatch, deg, E):
-    """The DMMA/TMA kernels (every shape with L <= 128, degree <= 15) and the column-stationary
-    DFMA kernels are two evaluations of the same folded sums: values agree to rounding,
-    per-pair minima follow their values."""
+    """The DMMA kernels (TMA-store variant for L <= 128, column-tiled variant above; degree <= 15)
+    and the column-stationary DFMA kernels are two evaluations of the same folded sums: values
+    agree to rounding, per-pair minima follow their values."""
     import torch
     from optimalbeziertrajectorygeneration_b200 import _capi, engine
     from oracle.make_golden import synthetic_swarm_args
@@ -243,8 +244,14 @@ def test_fused_gather_stores_on_one_gpu(gopt):
     x6 = torch.full((1, 6), float("nan"), dtype=torch.float64, device=e2.device)
     s7 = e2.separation(c2, 0, 0.9, pairmin=p6, peer_ptrs=[x6.data_ptr()])     # L = 7: tensor path since round 2
     assert torch.equal(p6, s7.min(dim=2).values) and torch.equal(x6, p6)
-    with pytest.raises(Exception):                       # L = 137: outside the tensor-path shapes
-        e2.separation(c2, 130, 0.9, pairmin=p6, peer_ptrs=[local.data_ptr()])
+    s137 = e2.separation(c2, 130, 0.9, pairmin=p6, peer_ptrs=[x6.data_ptr()])   # L = 137: column-tiled variant
+    assert torch.equal(p6, s137.min(dim=2).values) and torch.equal(x6, p6)
+    d1 = gopt.BezOptimization(numVeh=4, dimension=1, degree=3, initPoints=np.zeros((4, 1)),
+                              finalPoints=np.ones((4, 1)))
+    e1 = d1._engine(True)
+    c1, _ = e1.assemble(e1.upload(np.zeros((1, d1.nvar))), 0)
+    with pytest.raises(Exception):                       # dim 1: outside the tensor-path kernels
+        e1.separation(c1, 0, 0.9, pairmin=p6, peer_ptrs=[local.data_ptr()])
 
 
 def test_unaligned_and_ragged_outputs(gopt):
