@@ -500,7 +500,7 @@ def run_ours(opts):
     #  (d) the reference-facing closures: the full 508 MB constraint vector per x
     gopt.DEG_ELEV = E
     bezopt.zero_copy_results = True
-    nS = max(8, min(opts.steps, 40))
+    nS = max(16, min(2 * opts.steps, 64))
     Xs = np.concatenate([X] * nS, axis=0)
     for _ in range(2):
         act = bezopt.evaluate_sweep_active(Xs, elev=E, chunk=B)
