@@ -65,6 +65,30 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// --- TMA bulk load (global -> shared::cta), mbarrier completion --------------------
+__device__ __forceinline__ void mbar_init(unsigned mbar_s, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar_s, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar_s, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(mbar_s), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned sdst, const void *gsrc, unsigned bytes, unsigned mbar_s) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar_s) : "memory");
+}
+
 // Folded elevation weights in B-fragment order, register resident for the whole kernel.
 // NP = n-tile pairs of the shape: 16 NP column-pair slots cover Lh <= 16 NP, i.e. L <= 32 NP
 // (NP = 4: the headline shapes 65 <= L <= 128; NP = 2: 33..64; NP = 1: L <= 32).
@@ -134,9 +158,11 @@ __device__ __forceinline__ void emit_minima_item_order(const MinSinks &S, double
     }
     if (valid) {
         if (S.itemmin) S.itemmin[dst] = vi;
+        if (S.npeers > 0) {                                 // warp-uniform
 #pragma unroll
-        for (int q = 0; q < BEZ_MAX_PEERS; ++q)
-            if (q < S.npeers) S.peer_min[q][dst] = vi;
+            for (int q = 0; q < BEZ_MAX_PEERS; ++q)
+                if (q < S.npeers) S.peer_min[q][dst] = vi;
+        }
     }
     if (S.mask || S.list_count) {                       // warp-uniform
         const bool act = valid && vi < S.threshold;
@@ -164,11 +190,28 @@ __device__ __forceinline__ void emit_minima_item_order(const MinSinks &S, double
 // pair p+1 (4 independent accumulator chains, round-robin over the k-steps) are issued
 // before the epilogue of pair p, so the fp64 pipe always has independent work queued
 // behind the DADD/STS of the epilogue.
-template <int N_, int NP, int MINMODE, bool STORE>
+//
+// Deferred stores (early_store = false): the proxy fence and the bulk store of m-tile mi are
+// issued behind the first DMMA group of m-tile mi + 1.  `fence.proxy.async` lowers to
+// MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, which waits for the warp's outstanding shared-memory
+// stores; right behind the 32 STS of an epilogue that wait is ~130 cycles of an in-order warp
+// (ncu: long-scoreboard samples on the fence), a dozen DMMAs later it is free.
+// rows_free(): called once per tile when the staged rows are dead (the A fragments of the last
+// m-tile are in registers, a proxy fence has just been executed) -- the kernel starts the TMA
+// fetch of the next tile's vehicle rows into the same shared-memory region there.
+struct NoRowsHook { __device__ __forceinline__ void operator()() const {} };
+
+constexpr int kExpSignSelect = 1;   // candidate minimum = the stored value picked by the sign of so (no DADD)
+constexpr int kExpEmitFirst = 2;    // per-item minima are emitted before the last block's fence + bulk store
+constexpr int kExpNoFetchFence = 4; // (kernel) no extra proxy fence in front of the TMA row fetch
+constexpr int kExpIRowsSmem = 8;    // (kernel) the i rows of a tile are fetched with TMA as well
+
+template <int N_, int NP, int MINMODE, bool STORE, class RowsFree = NoRowsHook, int EXP = 0>
 __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
                                          const BFrags<N_, NP> &B, double *__restrict__ outg,
                                          const MinSinks &S, long long g0, int cnt,
-                                         int L, double beta, int lane, bool base_aligned) {
+                                         int L, double beta, int lane, bool base_aligned,
+                                         bool early_store = false, RowsFree rows_free = RowsFree()) {
     constexpr int KE = Geom<N_>::KE, KO = Geom<N_>::KO;
     const int g = lane >> 2, t = lane & 3;
     const int M = L - 1;
@@ -181,6 +224,25 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
     for (int ks = 0; ks < KE; ++ks) aE[ks] = ar[ks];
 #pragma unroll
     for (int ks = 0; ks < KO; ++ks) aO[ks] = ar[16 + ks];
+
+    // staged 8 x L block of m-tile mi -> HBM (one TMA bulk store)
+    auto store_block = [&](int mi) {
+        const unsigned par = (unsigned)mi & 1u;
+        fence_async_smem();                         // generic-proxy writes -> visible to the TMA read
+        __syncwarp();
+        const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
+        double *dst = outg + (size_t)8 * mi * L;
+        const unsigned bytes = (unsigned)(nrows * L) * 8u;
+        if (base_aligned && (nrows == 8 || (bytes & 15u) == 0)) {
+            if (lane == 0) { bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes); bulk_commit(); }
+        } else {                                    // odd row count x odd L or unaligned base
+            const double *ob = obuf + (size_t)par * 8 * L;
+            for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
+            if (lane == 0) bulk_commit();           // empty group keeps the count in step
+        }
+    };
+    bool rows_released = false;
+    int last_block = -1;
 
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
@@ -225,8 +287,15 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
                     }
                 }
                 if (MINMODE) {                              // min(se+so, se-so) = se - |so|, one DADD
-                    cand[u][0] = c[u][0] - fabs(c[u][2]);
-                    cand[u][1] = c[u][1] - fabs(c[u][3]);
+                    if (STORE && (EXP & kExpSignSelect)) {  // ... or the stored value the sign of so picks
+                        const double f0 = c[u][0] + c[u][2], m0 = c[u][0] - c[u][2];
+                        const double f1 = c[u][1] + c[u][3], m1 = c[u][1] - c[u][3];
+                        cand[u][0] = __double2hiint(c[u][2]) < 0 ? f0 : m0;
+                        cand[u][1] = __double2hiint(c[u][3]) < 0 ? f1 : m1;
+                    } else {
+                        cand[u][0] = c[u][0] - fabs(c[u][2]);
+                        cand[u][1] = c[u][1] - fabs(c[u][3]);
+                    }
                 }
             }
             if (MINMODE) mnp[p] = dmin(dmin(cand[0][0], cand[0][1]), dmin(cand[1][0], cand[1][1]));
@@ -234,10 +303,12 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
 
         mma_pair(0, C[0]);
         if (STORE) {
+            if (mi > 0 && !early_store) store_block(mi - 1);
             // the bulk read of this staging buffer (issued two m-tiles ago) must be done
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
         }
+        if (mi == 3) { rows_free(); rows_released = true; }
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             if (p < NP - 1) mma_pair(p + 1, C[(p + 1) & 1]);
@@ -256,21 +327,13 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
             for (int p = 1; p < NP; ++p) m = dmin(m, mnp[p]);
             mnv[mi] = m;
         }
-        if (STORE) {
-            fence_async_smem();                     // generic-proxy writes -> visible to the TMA read
-            __syncwarp();
-            const int nrows = (cnt - 8 * mi) < 8 ? (cnt - 8 * mi) : 8;
-            double *dst = outg + (size_t)8 * mi * L;
-            const unsigned bytes = (unsigned)(nrows * L) * 8u;
-            if (base_aligned && (nrows == 8 || (bytes & 15u) == 0)) {
-                if (lane == 0) { bulk_store(dst, obuf_s + par * (unsigned)(64 * L), bytes); bulk_commit(); }
-            } else {                                // odd row count x odd L or unaligned base
-                for (int i = lane; i < nrows * L; i += 32) __stcs(dst + i, ob[i]);
-                if (lane == 0) bulk_commit();       // empty group keeps the count in step
-            }
+        if (STORE && (early_store || mi == 3 || 8 * (mi + 1) >= cnt)) {
+            if ((EXP & kExpEmitFirst) && MINMODE && !early_store && (mi == 3 || 8 * (mi + 1) >= cnt)) last_block = mi;
+            else store_block(mi);
         }
     }
-    if (STORE && cnt <= 24) {                       // short tile: realign the buffer rotation
+    if (!rows_released) rows_free();                // short tile (the last one of a launch)
+    if (STORE && cnt <= 24 && last_block < 0) {     // short tile: realign the buffer rotation
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
     }
@@ -286,6 +349,13 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         const double r2 = __shfl_xor_sync(0xffffffffu, b1 ? a0 : a1, 2);
         const double v = dmin(b1 ? a1 : a0, r2);               // m-tile t
         emit_minima(S, v, g0, cnt, lane);
+    }
+    if (STORE && (EXP & kExpEmitFirst) && last_block >= 0) {
+        store_block(last_block);
+        if (cnt <= 24) {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        }
     }
 }
 

@@ -16,16 +16,41 @@ using namespace bezcore;
 // NP n-tile pairs cover 16 NP column-pair slots (NP = 4: 65 <= L <= 128, the headline shapes;
 // NP = 2: 33 <= L <= 64; NP = 1: L <= 32).  One warp = 32 items, no block-wide barriers in the
 // main loop; per warp 8.4 KB of staged rows + two [8][L] output staging buffers.
-template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE>
+//
+// TMAROWS (PAIR): the partner-vehicle rows of a tile (lane l: row j_l of evaluation b_l) are
+// contiguous runs of the control-point array -- one run while the tile stays inside a row of
+// the pair list -- so they are fetched with one `cp.async.bulk` (TMA) per run into the warp's
+// row region, completion on a per-warp mbarrier.  The fetch of tile t + 1 is issued from inside
+// the DMMA phase of tile t (mma_tile's rows_free hook: the region is shared with the staged
+// (e, o) rows and is dead once the last A fragments are in registers) and lands behind the last
+// m-tile.  Per-lane global loads of the same rows touch 32 different cache lines per LDG.128
+// (1088 L1 wavefronts per tile, l1tex throughput 66 %) and left the warp 9 % of its time on the
+// long scoreboard (profiles/r02_ncu_pair_kernel.txt); the i rows (one row for the whole tile
+// in general) stay on the L1-resident broadcast loads.
+template <int N_, int DIM> __host__ __device__ constexpr int region_doubles(bool tmarows) {
+    constexpr int S_ = (DIM * (N_ + 1) + 1) / 2 * 2;
+    return (tmarows && 32 * S_ > bezmma::kRowsDoubles) ? 32 * S_ : bezmma::kRowsDoubles;
+}
+
+template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE, bool TMAROWS, int EXP = 0>
 __global__ void __launch_bounds__(kThreads, 2)
 sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N_> DW) {
     using namespace bezmma;
+    static_assert(!TMAROWS || MODE == PAIR, "the TMA row fetch is for the pair kernel");
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t per_warp = (size_t)kRowsDoubles + (STORE ? 16 * (size_t)A.L : 0);
+    constexpr int kRegion = region_doubles<N_, DIM>(TMAROWS);
+    constexpr int S_ = (DIM * (N_ + 1) + 1) / 2 * 2;
+    const size_t per_warp = (size_t)kRegion + (STORE ? 16 * (size_t)A.L : 0);
     double *rows = smem + warp * per_warp;
-    double *obuf = rows + kRowsDoubles;
-    for (int i = lane; i < kRowsDoubles; i += 32) rows[i] = 0.0;     // padding slots must be 0
+    double *obuf = rows + kRegion;
+    const unsigned rows_s = (unsigned)__cvta_generic_to_shared(rows);
+    const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(smem + kWarps * per_warp) + 8u * warp;
+    if (TMAROWS) {
+        if (lane == 0) { mbar_init(mbar_s, 1); mbar_fence_init(); }
+    } else {
+        for (int i = lane; i < kRowsDoubles; i += 32) rows[i] = 0.0;     // padding slots must be 0
+    }
     const unsigned obuf_s = (unsigned)__cvta_generic_to_shared(obuf);
     BFrags<N_, NP> Bf;
     load_bfrags<N_, NP>(Bf, A.PQ, A.L, A.LhPad, lane);
@@ -47,12 +72,35 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
     const long long wt_end = strided ? nwt : (gwarp + 1) * nwt / nwarps;
     const long long wt_step = strided ? nwarps : 1;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(A.out) & 15u) == 0;
-    constexpr int S_ = (DIM * (N_ + 1) + 1) / 2 * 2;
+    const bool early_store = (A.flags & kFlagEarlyFence) != 0;
 
     PairCursor cur;
+    bool have_next = false;
+    unsigned phase = 0;
+    // TMA fetch of the rows c.j of all lanes (warp converged): one bulk copy per run of lanes
+    // whose rows are consecutive in memory; lane l's row lands at rows + l * S_
+    auto fetch_rows = [&]() {
+        if (!TMAROWS || !have_next) return;
+        const int pb = __shfl_up_sync(0xffffffffu, cur.b, 1), pi = __shfl_up_sync(0xffffffffu, cur.i, 1);
+        const int pj = __shfl_up_sync(0xffffffffu, cur.j, 1);
+        const bool start = lane == 0 || cur.b != pb || cur.i != pi || cur.j != pj + 1;
+        const unsigned runs = __ballot_sync(0xffffffffu, start);
+        // generic-proxy accesses of the region before the async-proxy writes
+        if (!((EXP & kExpNoFetchFence) && STORE)) fence_async_smem();
+        if (lane == 0) mbar_arrive_expect_tx(mbar_s, 32u * S_ * 8u);
+        __syncwarp();
+        if (start) {
+            const unsigned higher = lane == 31 ? 0u : (runs & (0xffffffffu << (lane + 1)));
+            const int end = higher ? __ffs(higher) - 1 : 32;
+            bulk_load(rows_s + (unsigned)lane * (S_ * 8u), A.cpts + ((size_t)cur.b * A.N + cur.j) * S_,
+                      (unsigned)(end - lane) * (S_ * 8u), mbar_s);
+        }
+    };
     if (MODE == PAIR && wt < wt_end) {
         const long long f = (wt << 5) + lane;
         cur = pair_cursor_at(A, f < total ? f : total - 1);
+        have_next = true;
+        fetch_rows();
     }
     for (; wt < wt_end; wt += wt_step) {
         const long long g0 = wt << 5;                          // first flattened item of the tile
@@ -60,11 +108,14 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
         {
             double s[2 * N_ + 1];
             if (MODE == PAIR) {
-                stage1_coeffs<N_, DIM, MODE>(A, PW, DW, cur.b, cur.i, cur.j, s);
+                if (TMAROWS) { mbar_wait(mbar_s, phase); phase ^= 1u; }
+                stage1_coeffs<N_, DIM, MODE, TMAROWS>(A, PW, DW, cur.b, cur.i, cur.j, s, rows + lane * S_);
+                if (TMAROWS) __syncwarp();                     // every lane has its row: the region is rewritten below
                 // this lane's item of the warp's next tile (lanes past the end of the list stay on
                 // the last item, so every staged row is finite)
                 const long long fn = g0 + (long long)wt_step * 32 + lane;
-                if (wt + wt_step < wt_end) {
+                have_next = wt + wt_step < wt_end;
+                if (have_next) {
                     if (wt_step == 1 && fn < total) cur = pair_cursor_next(A, cur, g0 + lane);
                     else cur = pair_cursor_at(A, fn < total ? fn : total - 1);
                     if (A.flags & kFlagPrefetchL1) {
@@ -91,17 +142,24 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
                 row[slot_o(j)] = s[j] - s[2 * N_ - j];
             }
             row[slot_e(N_)] = s[N_];
+            if (TMAROWS) {               // the fetched rows overwrite the padding slots of the k-steps
+#pragma unroll
+                for (int j = N_ + 1; j < 4 * Geom<N_>::KE; ++j) row[slot_e(j)] = 0.0;
+#pragma unroll
+                for (int j = N_; j < 4 * Geom<N_>::KO; ++j) row[slot_o(j)] = 0.0;
+            }
         }
         __syncwarp();
-        mma_tile<N_, NP, MINMODE, STORE>(rows, obuf, obuf_s, Bf, STORE ? A.out + (size_t)g0 * A.L : nullptr, A.sinks,
-                                         g0, cnt, A.L, A.beta, lane, base_aligned);
+        mma_tile<N_, NP, MINMODE, STORE, decltype(fetch_rows), EXP>(rows, obuf, obuf_s, Bf, STORE ? A.out + (size_t)g0 * A.L : nullptr,
+                                                                    A.sinks, g0, cnt, A.L, A.beta, lane, base_aligned, early_store,
+                                                                    fetch_rows);
         __syncwarp();
     }
     if (STORE && lane == 0) bulk_wait_all();      // staging buffers must outlive the last bulk reads
 }
 
-template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE>
-int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
+template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE, bool TMAROWS, int EXP = 0>
+int launch_sq_elev_mma_rows(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     ProdWeights<N_> PW;
     DiffWeights<N_> DW;
     const double scale = A.alpha * (0.5 * (double)DIM);       // Q1: dim/2 and the sign of alpha, folded
@@ -111,8 +169,8 @@ int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t s
             PW.w[widx<N_>(i, j)] = (i == j) ? w : 2.0 * w;
         }
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
-    const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + (STORE ? 16 * (size_t)A.L : 0)) * sizeof(double);
-    auto kern = sq_elev_mma_kernel<N_, DIM, MODE, NP, MINMODE, STORE>;
+    const size_t shmem = (size_t)kWarps * (region_doubles<N_, DIM>(TMAROWS) + (STORE ? 16 * (size_t)A.L : 0) + 1) * sizeof(double);
+    auto kern = sq_elev_mma_kernel<N_, DIM, MODE, NP, MINMODE, STORE, TMAROWS, EXP>;
     int sms = 148, per_sm = 1;
     if (int rc = bez_kernel_config((const void *)kern, kThreads, shmem, &sms, &per_sm)) return rc;
     const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
@@ -128,6 +186,27 @@ int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t s
     kern<<<(unsigned)grid, kThreads, shmem, st>>>(A, PW, DW);
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;
+}
+
+// The pair kernel fetches its partner rows with TMA; the per-lane global loads stay available
+// for A/B runs in development builds (BEZGPU_MMA_FLAGS bit 4).
+template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE>
+int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
+    if constexpr (MODE == PAIR) {
+#ifdef BEZ_ONLY_N
+        if (A.flags & kFlagRowsByLdg) return launch_sq_elev_mma_rows<N_, DIM, MODE, NP, MINMODE, STORE, false>(plan, A, st);
+        if constexpr (NP == 4 && STORE && MINMODE) {         // experiments: BEZGPU_MMA_FLAGS = exp << 8
+            switch ((A.flags >> 8) & 0xff) {
+#define BEZ_EXP(e) case e: return launch_sq_elev_mma_rows<N_, DIM, MODE, NP, MINMODE, STORE, true, e>(plan, A, st);
+                BEZ_EXP(1) BEZ_EXP(2) BEZ_EXP(4) BEZ_EXP(6) BEZ_EXP(7)
+#undef BEZ_EXP
+            }
+        }
+#endif
+        return launch_sq_elev_mma_rows<N_, DIM, MODE, NP, MINMODE, STORE, true>(plan, A, st);
+    } else {
+        return launch_sq_elev_mma_rows<N_, DIM, MODE, NP, MINMODE, STORE, false>(plan, A, st);
+    }
 }
 
 // rows + minima / rows only / minima only (the combination "neither" is rejected by the caller)

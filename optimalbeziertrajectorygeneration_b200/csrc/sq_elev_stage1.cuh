@@ -25,7 +25,10 @@ struct SqElevArgs {
 };
 constexpr int kFlagPrefetchL1 = 1;     // prefetch.global.L1 of the next tile's vehicle rows
 constexpr int kFlagStridedTiles = 2;   // round-1 tile order (warp-strided, full decode per tile)
-// (bits 4 and 8 were the round-2 ablations "no TMA store" / "no fence": profiles/r02_ablation_pair_kernel.txt)
+// (bits 4 and 8 were the round-2 ablations "no TMA store" / "no fence": profiles/r02_ablation_pair_kernel.txt;
+//  reused since:)
+constexpr int kFlagRowsByLdg = 4;      // A/B: partner rows through per-lane global loads (no TMA row fetch)
+constexpr int kFlagEarlyFence = 8;     // A/B: proxy fence + bulk store right behind an m-tile's epilogue
 constexpr int kFlagFullGridWithPeers = 16;   // A/B: do not leave a CTA slot free for the completion barrier
 constexpr int kFlagFusedList = 64;     // A/B: append the active list from the epilogue even in large launches
 constexpr int kFlagTeam = 32;          // 65 <= L <= 128: third-generation team kernel (sq_elev_team.cuh)
@@ -63,21 +66,25 @@ __device__ __forceinline__ PairCursor pair_cursor_next(const SqElevArgs &A, cons
 // li = item index inside the tile; lanes past the end recompute the last item so
 // every staged row is finite.
 // PAIR: (vi, vj) = the pair; SPEED: vi = the vehicle.
-template <int N_, int DIM, int MODE>
+// JROW_SMEM (PAIR only): row vj has already been brought into shared memory (jrow, 16-byte
+// aligned; the TMA row fetch of sq_elev_mma_kernel.cuh) and is read with LDS.128 instead of
+// 17 global loads whose 32 lanes touch 32 different cache lines each.
+template <int N_, int DIM, int MODE, bool JROW_SMEM = false>
 __device__ __forceinline__ void stage1_coeffs(const SqElevArgs &A, const ProdWeights<N_> &PW,
                                               const DiffWeights<N_> &DW, int b, int vi, int vj,
-                                              double (&s)[2 * N_ + 1]) {
+                                              double (&s)[2 * N_ + 1], const double *jrow = nullptr) {
     constexpr int NC = N_ + 1;
     constexpr int S = (DIM * NC + 1) / 2 * 2;                 // doubles per vehicle row (16 B aligned)
     const double *base = A.cpts + (size_t)b * ((size_t)S * A.N);
     double a[DIM][NC];
     if (MODE == PAIR) {
         const double2 *pi = reinterpret_cast<const double2 *>(base + (size_t)vi * S);
-        const double2 *pj = reinterpret_cast<const double2 *>(base + (size_t)vj * S);
+        const double2 *pj = JROW_SMEM ? reinterpret_cast<const double2 *>(jrow)
+                                      : reinterpret_cast<const double2 *>(base + (size_t)vj * S);
         double *af = &a[0][0];
 #pragma unroll
         for (int q = 0; q < S / 2; ++q) {                      // Bezier.sub
-            const double2 u = __ldg(pi + q), w = __ldg(pj + q);
+            const double2 u = __ldg(pi + q), w = JROW_SMEM ? pj[q] : __ldg(pj + q);
             if (2 * q < DIM * NC) af[2 * q] = u.x - w.x;
             if (2 * q + 1 < DIM * NC) af[2 * q + 1] = u.y - w.y;
         }

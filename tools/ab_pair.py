@@ -1,5 +1,7 @@
 """A/B timing of the fused pair kernel on the C4 workload: kernel flags (BEZGPU_MMA_FLAGS:
-1 = L1 prefetch of the next tile's rows, 2 = round-1 strided tile order) x output variants.
+1 = L1 prefetch of the next tile's rows, 2 = round-1 strided tile order, 4 = partner rows by per-lane
+global loads instead of the TMA row fetch (development builds only), 8 = proxy fence + bulk store right
+behind each m-tile's epilogue instead of deferred) x output variants.
 usage: python tools/ab_pair.py [B] [reps]"""
 import os
 import sys
@@ -49,20 +51,34 @@ variants = {
     "rows+min+mask+list": lambda: (act.reset(), eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm, active=act)),
     "min only (no rows)": lambda: eng.separation(cpts, E, args["maxSep"], pairmin=pm, rows=False),
 }
-for flags in os.environ.get("AB_FLAGS", "0,2,1").split(","):
-    os.environ["BEZGPU_MMA_FLAGS"] = flags
-    for name, fn in variants.items():
-        ms = timeit(fn)
-        print("flags=%s %-20s mean %.4f ms  min %.4f ms  -> %.0f GB/s = %.3f of 6484.6" %
-              (flags, name, ms.mean(), ms.min(), gb / (ms.mean() * 1e-3), gb / (ms.mean() * 1e-3) / 6484.6), flush=True)
+# Round-robin over (flags, variant) inside every repetition: a box slows down by 2-3 % over the first
+# seconds of sustained fp64 load, so variants timed one after the other are not comparable.
+flag_list = os.environ.get("AB_FLAGS", "0,2,1").split(",")
+combos = [(fl, name) for fl in flag_list for name in variants]
+times = {c: [] for c in combos}
+for r in range(reps + 3):
+    evs = []
+    for fl, name in combos:
+        os.environ["BEZGPU_MMA_FLAGS"] = fl
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        variants[name]()
+        b.record()
+        evs.append((fl, name, a, b))
+    torch.cuda.synchronize()
+    if r >= 3:
+        for fl, name, a, b in evs:
+            times[(fl, name)].append(a.elapsed_time(b))
+for fl, name in combos:
+    ms = np.array(times[(fl, name)])
+    print("flags=%s %-20s mean %.4f ms  min %.4f ms  -> %.0f GB/s = %.3f of 6484.6" %
+          (fl, name, ms.mean(), ms.min(), gb / (ms.mean() * 1e-3), gb / (ms.mean() * 1e-3) / 6484.6), flush=True)
 os.environ["BEZGPU_MMA_FLAGS"] = "0"
 eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm)
 print("min == row min:", bool(torch.equal(pm, out.min(dim=2).values)), " active pairs:", int((pm < 0).sum()))
 # every flag set must reproduce the flags=0 bits (values, minima, mask, list)
 ref_out, ref_pm = out[:1].clone(), pm.clone()
 for flags in os.environ.get("AB_FLAGS", "0,2,1").split(","):
-    if int(flags) & 12:
-        continue                                    # ablations: wrong by construction
     os.environ["BEZGPU_MMA_FLAGS"] = flags
     out.fill_(float("nan")); pm.fill_(float("nan")); act.reset()
     eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm, active=act)
