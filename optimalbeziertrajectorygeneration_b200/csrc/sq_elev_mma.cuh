@@ -201,12 +201,7 @@ __device__ __forceinline__ void emit_minima_item_order(const MinSinks &S, double
 // fetch of the next tile's vehicle rows into the same shared-memory region there.
 struct NoRowsHook { __device__ __forceinline__ void operator()() const {} };
 
-constexpr int kExpSignSelect = 1;   // candidate minimum = the stored value picked by the sign of so (no DADD)
-constexpr int kExpEmitFirst = 2;    // per-item minima are emitted before the last block's fence + bulk store
-constexpr int kExpNoFetchFence = 4; // (kernel) no extra proxy fence in front of the TMA row fetch
-constexpr int kExpIRowsSmem = 8;    // (kernel) the i rows of a tile are fetched with TMA as well
-
-template <int N_, int NP, int MINMODE, bool STORE, class RowsFree = NoRowsHook, int EXP = 0>
+template <int N_, int NP, int MINMODE, bool STORE, class RowsFree = NoRowsHook, int MT_UNROLL = 4>
 __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsigned obuf_s,
                                          const BFrags<N_, NP> &B, double *__restrict__ outg,
                                          const MinSinks &S, long long g0, int cnt,
@@ -242,11 +237,13 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         }
     };
     bool rows_released = false;
-    int last_block = -1;
 
-#pragma unroll
+#pragma unroll(MT_UNROLL)
     for (int mi = 0; mi < 4; ++mi) {
-        if (8 * mi >= cnt) break;
+        if (8 * mi >= cnt) {                        // short tile (the last one of a launch)
+            mnv[0] = mnv[1]; mnv[1] = mnv[2]; mnv[2] = mnv[3]; mnv[3] = INFINITY;
+            continue;
+        }
         // staging buffer mi & 1: every tile but the very last of a launch has 4 m-tiles (the
         // tiles run over the flattened item list), so the parity is a compile-time constant;
         // a short tile drains the bulk groups at its end (below)
@@ -287,15 +284,8 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
                     }
                 }
                 if (MINMODE) {                              // min(se+so, se-so) = se - |so|, one DADD
-                    if (STORE && (EXP & kExpSignSelect)) {  // ... or the stored value the sign of so picks
-                        const double f0 = c[u][0] + c[u][2], m0 = c[u][0] - c[u][2];
-                        const double f1 = c[u][1] + c[u][3], m1 = c[u][1] - c[u][3];
-                        cand[u][0] = __double2hiint(c[u][2]) < 0 ? f0 : m0;
-                        cand[u][1] = __double2hiint(c[u][3]) < 0 ? f1 : m1;
-                    } else {
-                        cand[u][0] = c[u][0] - fabs(c[u][2]);
-                        cand[u][1] = c[u][1] - fabs(c[u][3]);
-                    }
+                    cand[u][0] = c[u][0] - fabs(c[u][2]);
+                    cand[u][1] = c[u][1] - fabs(c[u][3]);
                 }
             }
             if (MINMODE) mnp[p] = dmin(dmin(cand[0][0], cand[0][1]), dmin(cand[1][0], cand[1][1]));
@@ -325,15 +315,14 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
             double m = mnp[0];
 #pragma unroll
             for (int p = 1; p < NP; ++p) m = dmin(m, mnp[p]);
-            mnv[mi] = m;
+            // mnv[k] = minimum of m-tile k after the fourth pass (static register indices even
+            // when the loop is not unrolled)
+            mnv[0] = mnv[1]; mnv[1] = mnv[2]; mnv[2] = mnv[3]; mnv[3] = m;
         }
-        if (STORE && (early_store || mi == 3 || 8 * (mi + 1) >= cnt)) {
-            if ((EXP & kExpEmitFirst) && MINMODE && !early_store && (mi == 3 || 8 * (mi + 1) >= cnt)) last_block = mi;
-            else store_block(mi);
-        }
+        if (STORE && (early_store || mi == 3 || 8 * (mi + 1) >= cnt)) store_block(mi);
     }
     if (!rows_released) rows_free();                // short tile (the last one of a launch)
-    if (STORE && cnt <= 24 && last_block < 0) {     // short tile: realign the buffer rotation
+    if (STORE && cnt <= 24) {                       // short tile: realign the buffer rotation
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
     }
@@ -349,13 +338,6 @@ __device__ __forceinline__ void mma_tile(const double *rows, double *obuf, unsig
         const double r2 = __shfl_xor_sync(0xffffffffu, b1 ? a0 : a1, 2);
         const double v = dmin(b1 ? a1 : a0, r2);               // m-tile t
         emit_minima(S, v, g0, cnt, lane);
-    }
-    if (STORE && (EXP & kExpEmitFirst) && last_block >= 0) {
-        store_block(last_block);
-        if (cnt <= 24) {
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
-        }
     }
 }
 

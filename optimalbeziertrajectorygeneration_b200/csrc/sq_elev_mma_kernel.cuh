@@ -6,8 +6,8 @@
 #include <stdlib.h>
 
 #include "sq_elev_stage1.cuh"
-#include "sq_elev_team.cuh"
 #include "sq_elev_mma_wide.cuh"
+#include "sq_elev_ws.cuh"
 
 namespace bezmma_inst {
 using namespace bezcore;
@@ -32,7 +32,7 @@ template <int N_, int DIM> __host__ __device__ constexpr int region_doubles(bool
     return (tmarows && 32 * S_ > bezmma::kRowsDoubles) ? 32 * S_ : bezmma::kRowsDoubles;
 }
 
-template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE, bool TMAROWS, int EXP = 0>
+template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE, bool TMAROWS>
 __global__ void __launch_bounds__(kThreads, 2)
 sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeights<N_> DW) {
     using namespace bezmma;
@@ -85,8 +85,7 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
         const int pj = __shfl_up_sync(0xffffffffu, cur.j, 1);
         const bool start = lane == 0 || cur.b != pb || cur.i != pi || cur.j != pj + 1;
         const unsigned runs = __ballot_sync(0xffffffffu, start);
-        // generic-proxy accesses of the region before the async-proxy writes
-        if (!((EXP & kExpNoFetchFence) && STORE)) fence_async_smem();
+        fence_async_smem();             // generic-proxy accesses of the region before the async-proxy writes
         if (lane == 0) mbar_arrive_expect_tx(mbar_s, 32u * S_ * 8u);
         __syncwarp();
         if (start) {
@@ -150,15 +149,15 @@ sq_elev_mma_kernel(const SqElevArgs A, const ProdWeights<N_> PW, const DiffWeigh
             }
         }
         __syncwarp();
-        mma_tile<N_, NP, MINMODE, STORE, decltype(fetch_rows), EXP>(rows, obuf, obuf_s, Bf, STORE ? A.out + (size_t)g0 * A.L : nullptr,
-                                                                    A.sinks, g0, cnt, A.L, A.beta, lane, base_aligned, early_store,
-                                                                    fetch_rows);
+        mma_tile<N_, NP, MINMODE, STORE, decltype(fetch_rows)>(rows, obuf, obuf_s, Bf, STORE ? A.out + (size_t)g0 * A.L : nullptr,
+                                                               A.sinks, g0, cnt, A.L, A.beta, lane, base_aligned, early_store,
+                                                               fetch_rows);
         __syncwarp();
     }
     if (STORE && lane == 0) bulk_wait_all();      // staging buffers must outlive the last bulk reads
 }
 
-template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE, bool TMAROWS, int EXP = 0>
+template <int N_, int DIM, int MODE, int NP, int MINMODE, bool STORE, bool TMAROWS>
 int launch_sq_elev_mma_rows(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     ProdWeights<N_> PW;
     DiffWeights<N_> DW;
@@ -170,7 +169,7 @@ int launch_sq_elev_mma_rows(const bez_plan *plan, const SqElevArgs &A, cudaStrea
         }
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
     const size_t shmem = (size_t)kWarps * (region_doubles<N_, DIM>(TMAROWS) + (STORE ? 16 * (size_t)A.L : 0) + 1) * sizeof(double);
-    auto kern = sq_elev_mma_kernel<N_, DIM, MODE, NP, MINMODE, STORE, TMAROWS, EXP>;
+    auto kern = sq_elev_mma_kernel<N_, DIM, MODE, NP, MINMODE, STORE, TMAROWS>;
     int sms = 148, per_sm = 1;
     if (int rc = bez_kernel_config((const void *)kern, kThreads, shmem, &sms, &per_sm)) return rc;
     const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
@@ -195,13 +194,6 @@ int launch_sq_elev_mma(const bez_plan *plan, const SqElevArgs &A, cudaStream_t s
     if constexpr (MODE == PAIR) {
 #ifdef BEZ_ONLY_N
         if (A.flags & kFlagRowsByLdg) return launch_sq_elev_mma_rows<N_, DIM, MODE, NP, MINMODE, STORE, false>(plan, A, st);
-        if constexpr (NP == 4 && STORE && MINMODE) {         // experiments: BEZGPU_MMA_FLAGS = exp << 8
-            switch ((A.flags >> 8) & 0xff) {
-#define BEZ_EXP(e) case e: return launch_sq_elev_mma_rows<N_, DIM, MODE, NP, MINMODE, STORE, true, e>(plan, A, st);
-                BEZ_EXP(1) BEZ_EXP(2) BEZ_EXP(4) BEZ_EXP(6) BEZ_EXP(7)
-#undef BEZ_EXP
-            }
-        }
 #endif
         return launch_sq_elev_mma_rows<N_, DIM, MODE, NP, MINMODE, STORE, true>(plan, A, st);
     } else {
@@ -214,11 +206,13 @@ template <int N_, int DIM, int MODE, int NP>
 int mma_dispatch_variant(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st) {
     const bezmma::MinSinks &S = A.sinks;
     const bool wm = S.itemmin || S.mask || S.list_count || S.npeers > 0;
-    if constexpr (NP == 4) {
-        if (A.flags & kFlagTeam) {
-            if (A.out == nullptr) return bezteam::launch_sq_elev_team<N_, DIM, MODE, 1, false>(plan, A, st);
-            return wm ? bezteam::launch_sq_elev_team<N_, DIM, MODE, 1, true>(plan, A, st)
-                      : bezteam::launch_sq_elev_team<N_, DIM, MODE, 0, true>(plan, A, st);
+    // the headline shapes (pair rows, 65 <= L <= 128) run warp-specialised whenever the three row
+    // slots per scheduler and the consumers' staging buffers fit the SM's shared memory
+    if constexpr (NP == 4 && MODE == PAIR) {
+        if (!(A.flags & kFlagNoWarpSpecialisation) && bezws::ws_fits<N_, DIM>(A.L, A.out != nullptr)) {
+            if (A.out == nullptr) return bezws::launch_sq_elev_ws<N_, DIM, 1, false>(plan, A, st);
+            return wm ? bezws::launch_sq_elev_ws<N_, DIM, 1, true>(plan, A, st)
+                      : bezws::launch_sq_elev_ws<N_, DIM, 0, true>(plan, A, st);
         }
     }
     if (A.out == nullptr) {

@@ -31,7 +31,8 @@ constexpr int kFlagRowsByLdg = 4;      // A/B: partner rows through per-lane glo
 constexpr int kFlagEarlyFence = 8;     // A/B: proxy fence + bulk store right behind an m-tile's epilogue
 constexpr int kFlagFullGridWithPeers = 16;   // A/B: do not leave a CTA slot free for the completion barrier
 constexpr int kFlagFusedList = 64;     // A/B: append the active list from the epilogue even in large launches
-constexpr int kFlagTeam = 32;          // 65 <= L <= 128: third-generation team kernel (sq_elev_team.cuh)
+constexpr int kFlagNoWarpSpecialisation = 128;  // A/B: 65 <= L <= 128 pair rows on the 8-warp kernel instead of sq_elev_ws.cuh
+// (bit 32 was the third-generation "team" kernel: profiles/r02_ablation_pair_kernel.txt)
 
 
 // Position of a lane's item in the lexicographic pair list, advanced incrementally from tile

@@ -5,6 +5,7 @@ behind each m-tile's epilogue instead of deferred) x output variants.
 usage: python tools/ab_pair.py [B] [reps]"""
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -31,6 +32,8 @@ gb = 8.0 * B * (P * L + P + 34 * N) / 1e9
 
 
 def timeit(fn):
+    if not os.environ.get("AB_HOT"):
+        time.sleep(0.4)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -51,28 +54,31 @@ variants = {
     "rows+min+mask+list": lambda: (act.reset(), eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm, active=act)),
     "min only (no rows)": lambda: eng.separation(cpts, E, args["maxSep"], pairmin=pm, rows=False),
 }
-# Round-robin over (flags, variant) inside every repetition: a box slows down by 2-3 % over the first
-# seconds of sustained fp64 load, so variants timed one after the other are not comparable.
+# Under sustained fp64 load a B200 slows down (2-3 % over the first seconds, 15 % after 2 s of
+# back-to-back launches: rows+min 0.36 -> 0.42 ms), and a kernel timed right behind a different one
+# inherits its dirty L2 lines.  bench.py times short bursts (20 steps = 8 ms), so the comparison is
+# made in that regime: every (flags, variant) block = idle pause, 3 warm-up launches, `reps` identical
+# launches; AB_ROUNDS cycles through the combinations (their spread is the noise floor).
+# AB_HOT=1 measures the sustained regime instead.
 flag_list = os.environ.get("AB_FLAGS", "0,2,1").split(",")
-combos = [(fl, name) for fl in flag_list for name in variants]
-times = {c: [] for c in combos}
-for r in range(reps + 3):
-    evs = []
+only = os.environ.get("AB_VARIANTS")
+names = [n for n in variants if not only or n in only.split(",")]
+combos = [(fl, name) for fl in flag_list for name in names]
+if os.environ.get("AB_HOT"):                  # sustained-load regime: ~2 s of back-to-back launches first
+    os.environ["BEZGPU_MMA_FLAGS"] = flag_list[0]
+    for _ in range(5000):
+        variants[names[0]]()
+    torch.cuda.synchronize()
+rounds = int(os.environ.get("AB_ROUNDS", "3"))
+res = {c: [] for c in combos}
+for r in range(rounds):
     for fl, name in combos:
         os.environ["BEZGPU_MMA_FLAGS"] = fl
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        variants[name]()
-        b.record()
-        evs.append((fl, name, a, b))
-    torch.cuda.synchronize()
-    if r >= 3:
-        for fl, name, a, b in evs:
-            times[(fl, name)].append(a.elapsed_time(b))
+        res[(fl, name)].append(timeit(variants[name]).mean())
 for fl, name in combos:
-    ms = np.array(times[(fl, name)])
-    print("flags=%s %-20s mean %.4f ms  min %.4f ms  -> %.0f GB/s = %.3f of 6484.6" %
-          (fl, name, ms.mean(), ms.min(), gb / (ms.mean() * 1e-3), gb / (ms.mean() * 1e-3) / 6484.6), flush=True)
+    ms = np.array(res[(fl, name)])
+    print("flags=%s %-20s %s  mean %.4f ms -> %.0f GB/s = %.3f of 6484.6" %
+          (fl, name, " ".join("%.4f" % v for v in ms), ms.mean(), gb / (ms.mean() * 1e-3), gb / (ms.mean() * 1e-3) / 6484.6), flush=True)
 os.environ["BEZGPU_MMA_FLAGS"] = "0"
 eng.separation(cpts, E, args["maxSep"], out=out, pairmin=pm)
 print("min == row min:", bool(torch.equal(pm, out.min(dim=2).values)), " active pairs:", int((pm < 0).sum()))
