@@ -467,8 +467,8 @@ def run_ours(opts):
                 "gather": gather_mode,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                             "kernel": "sq_elev_mma_kernel<10,3,PAIR,4 n-tile pairs,min,rows> (DMMA.8x8x4 stage 2, "
-                                       "TMA bulk-store epilogue)",
+                             "kernel": "sq_elev_ws_kernel<10,3,min,rows>: warp-specialised pair kernel (producer warps: TMA row "
+                                       "fetch + stage 1; consumer warps: DMMA.8x8x4 stage 2, fused minimum, TMA bulk-store epilogue)",
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                              "pipelined": None if kms_pipe is None else {
                                  "ms_per_launch": kms_pipe, "achieved": alg_bytes / (kms_pipe * 1e-3) / 1e9,
