@@ -22,6 +22,7 @@
 
 #include "sq_elev_core.cuh"
 #include "sq_elev_mma.cuh"
+#include "sq_elev_ws.cuh"
 
 namespace {
 using namespace bezcore;
@@ -32,6 +33,7 @@ template <int N_>
 struct FullWeights { double w[(N_ + 1) * (N_ + 1)]; };
 
 struct JacArgs {
+    int early_store;      // A/B: proxy fence + bulk store right behind each m-tile (BEZGPU_MMA_FLAGS bit 8)
     const double *cpts;   // [N][S] base point
     const double *dir;    // [N][S] d y / d x_kdir (DIR modes)
     const double *dx;     // [nvar]
@@ -258,10 +260,105 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
         }
         __syncwarp();
         mma_tile<N_, 4, 0, true>(rows, obuf, obuf_s, Bf, A.out + (size_t)t0 * A.L, no_sinks, t0, cnt, A.L, 0.0, lane,
-                                 base_aligned);
+                                 base_aligned, A.early_store != 0);
         __syncwarp();
     }
     if (lane == 0) bulk_wait_all();
+}
+
+// The same sweep kernel, warp-specialised like the pair kernel (sq_elev_ws.cuh): per scheduler one
+// producer warp (stage 1 only) feeds two consumer warps (DMMA stage 2 + TMA bulk stores) through a
+// ring of three row slots; no TMA row fetch here, the items of a tile read scattered rows.
+template <int N_, int DIM, int JMODE>
+__global__ void __launch_bounds__(bezws::kWsThreads, 1)
+jac_sq_elev_ws_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeights<N_> DW) {
+    using namespace bezmma;
+    using namespace bezws;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int group = warp & 3;
+    double *slots = smem + (size_t)group * kSlots * kRowsDoubles;
+    double *stag0 = smem + (size_t)4 * kSlots * kRowsDoubles;
+    const size_t stag_per = 16 * (size_t)A.L;
+    const unsigned bars_s = (unsigned)__cvta_generic_to_shared(stag0 + kConsumers * stag_per) + 8u * kBarsPerGroup * group;
+    auto full_b = [&](int s) { return bars_s + 8u * s; };
+    auto empty_b = [&](int s) { return bars_s + 8u * (kSlots + s); };
+    if (warp < kProducers) {
+        for (int i = lane; i < kSlots * kRowsDoubles; i += 32) slots[i] = 0.0;     // padding slots must be 0
+        if (lane == 0) {
+            for (int s = 0; s < kSlots; ++s) { mbar_init(full_b(s), 32); mbar_init(empty_b(s), 32); }
+            mbar_fence_init();
+        }
+    }
+    __syncthreads();
+    const long long nwt = (A.nitems + 31) >> 5;
+    const long long ngroups = (long long)gridDim.x * 4, gidx = (long long)blockIdx.x * 4 + group;
+    const long long t_begin = gidx * nwt / ngroups;
+    const int n = (int)((gidx + 1) * nwt / ngroups - t_begin);
+    if (warp < kProducers) {
+        reg_dec<120>();
+        for (int k = 0; k < n; ++k) {
+            const int s = k % kSlots, use = k / kSlots;
+            const long long t0 = (t_begin + k) << 5;
+            const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
+            double sc[2 * N_ + 1];
+            long long ro;
+            jac_stage1<N_, DIM, JMODE>(A, FW, DW, t0 + (lane < cnt ? lane : cnt - 1), sc, ro);
+            if (use > 0) mbar_wait(empty_b(s), (unsigned)(use - 1) & 1u);
+            double *row = slots + (size_t)s * kRowsDoubles + lane * kRowStride;
+#pragma unroll
+            for (int j = 0; j < N_; ++j) {
+                const double lo = sc[j] * A.scale, hi = sc[2 * N_ - j] * A.scale;
+                row[slot_e(j)] = lo + hi;
+                row[slot_o(j)] = lo - hi;
+            }
+            row[slot_e(N_)] = sc[N_] * A.scale;
+            mbar_arrive(full_b(s));
+        }
+    } else {
+        reg_inc<192>();
+        const int cidx = warp - kProducers, ci = cidx >> 2;
+        double *obuf = stag0 + (size_t)cidx * stag_per;
+        const unsigned obuf_s = (unsigned)__cvta_generic_to_shared(obuf);
+        const bool base_aligned = (reinterpret_cast<uintptr_t>(A.out) & 15u) == 0;
+        BFrags<N_, 4> Bf;
+        load_bfrags<N_, 4>(Bf, A.PQ, A.L, A.LhPad, lane);
+        MinSinks no_sinks;
+        memset(&no_sinks, 0, sizeof(no_sinks));
+        for (int k = ci; k < n; k += 2) {
+            const int s = k % kSlots, use = k / kSlots;
+            const long long t0 = (t_begin + k) << 5;
+            const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
+            mbar_wait(full_b(s), (unsigned)use & 1u);
+            auto release = [&]() { mbar_arrive(empty_b(s)); };
+            mma_tile<N_, 4, 0, true, decltype(release)>(slots + (size_t)s * kRowsDoubles, obuf, obuf_s, Bf,
+                                                        A.out + (size_t)t0 * A.L, no_sinks, t0, cnt, A.L, 0.0, lane,
+                                                        base_aligned, false, release);
+            __syncwarp();
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+}
+
+template <int N_, int DIM, int JMODE>
+int launch_jac_ws(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
+    FullWeights<N_> FW;
+    DiffWeights<N_> DW;
+    for (int i = 0; i < (N_ + 1) * (N_ + 1); ++i) FW.w[i] = plan->h_W[i];
+    for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
+    const size_t shmem = ((size_t)4 * bezws::kSlots * bezmma::kRowsDoubles + (size_t)bezws::kConsumers * 16 * A.L +
+                          4 * bezws::kBarsPerGroup) * sizeof(double);
+    auto kern = jac_sq_elev_ws_kernel<N_, DIM, JMODE>;
+    int sms = 148, per_sm = 1;
+    if (int rc = bez_kernel_config((const void *)kern, bezws::kWsThreads, shmem, &sms, &per_sm)) return rc;
+    const long long nwt = (A.nitems + 31) / 32;
+    long long grid = sms;
+    if (grid > (nwt + 7) / 8) grid = (nwt + 7) / 8;
+    if (grid < 1) return BEZ_OK;
+    kern<<<(unsigned)grid, bezws::kWsThreads, shmem, st>>>(A, FW, DW);
+    BEZ_CUDA(cudaGetLastError());
+    return BEZ_OK;
 }
 
 template <int N_, int DIM, int JMODE>
@@ -270,6 +367,11 @@ int launch_jac_mma(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
     DiffWeights<N_> DW;
     for (int i = 0; i < (N_ + 1) * (N_ + 1); ++i) FW.w[i] = plan->h_W[i];
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
+    const size_t ws_shmem = ((size_t)4 * bezws::kSlots * bezmma::kRowsDoubles + (size_t)bezws::kConsumers * 16 * A.L +
+                             4 * bezws::kBarsPerGroup) * sizeof(double);
+    // measured (tools/prof_jac.py): 7.1 ms against 5.0 ms -- one producer cannot feed two consumers here, its stage 1
+    // waits for scattered global loads tile after tile; kept behind BEZGPU_MMA_FLAGS bit 256 as an experiment
+    if (ws_shmem <= 232448 && (bez_sq_elev_mma_flags() & 256)) return launch_jac_ws<N_, DIM, JMODE>(plan, A, st);
     const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L) * sizeof(double);
     auto kern = jac_sq_elev_mma_kernel<N_, DIM, JMODE>;
     int sms = 148, per_sm = 1;
@@ -352,6 +454,7 @@ int fill_common(const bez_plan *plan, JacArgs &A, const double *d_cpts, const do
     A.cpts = d_cpts; A.dir = d_dir; A.dx = d_dx; A.PQ = plan->d_PQ; A.out = d_out;
     A.ld = ld; A.N = N; A.numVeh = numVeh; A.L = plan->L; A.Lh = plan->Lh; A.LhPad = plan->LhPad;
     A.ncols = ncols; A.offset = offset; A.kdir = kdir; A.dense = dense; A.tf = 1.0; A.scale = 1.0;
+    A.early_store = (bez_sq_elev_mma_flags() & kFlagEarlyFence) ? 1 : 0;
     return BEZ_OK;
 }
 
