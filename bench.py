@@ -822,7 +822,11 @@ def c5_measure(opts, world, rank, local, steps):
             "steps": steps, "ms_per_step": ms / steps, "kernel_ms": parts,
             "hbm_frac_whole_step": alg_eval * M * nv1 / (ms / steps * 1e-3) / 1e9 / peak,
             "angrate_fp64_frac": fma_eval * M * nv1 / (parts["angrate"] * 1e-3) / (64 * 148 * 1.965e9),
-            "separation_hbm_frac": 8.0 * pb.npairs_x * L * M * nv1 / (parts["separation"] * 1e-3) / 1e9 / peak,
+            # rows written + the control-point rows of every evaluation read once (16 obstacle rows + the
+            # vehicle row per evaluation: the 392 MB input of 131 072 evaluations does not stay in L2)
+            "separation_hbm_frac": 8.0 * (pb.npairs_x * L + (pb.npairs_x + 1) * 2 * (deg + 1)) * M * nv1
+                                   / (parts["separation"] * 1e-3) / 1e9 / peak,
+            "separation_hbm_frac_rows_only": 8.0 * pb.npairs_x * L * M * nv1 / (parts["separation"] * 1e-3) / 1e9 / peak,
             "gpu_launches": 4 * steps,
             "workload": "C5 synthetic Dubins batch: %d problems per GPU x (nvar+1 = %d) FD points, 1 vehicle + 16 "
                         "point obstacles, dim 2, degree 10, DEG_ELEV 100: 16 separation rows + max-speed row + "

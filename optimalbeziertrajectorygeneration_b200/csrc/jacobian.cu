@@ -51,10 +51,31 @@ struct JacArgs {
 
 // Stage 1 of the Jacobian kernels for one item: s = B(2a + dx*delta, delta) (unscaled) and
 // the offset of the item's output row.
+// J_PAIR_VAR item = (variable kk, partner curve u): owner vehicle v, dimension d, control point c
+struct PairVarItem { long long kk; int v, d, c, u; };
+__device__ __forceinline__ PairVarItem pair_var_item(const JacArgs &A, int dim, long long item) {
+    PairVarItem it;
+    const int dim_ncols = dim * A.ncols;
+    it.kk = item / (A.N - 1);
+    const int uu = (int)(item - it.kk * (A.N - 1));
+    it.v = (int)(it.kk / dim_ncols);
+    const int rem = (int)(it.kk - (long long)it.v * dim_ncols);
+    it.d = rem / A.ncols;
+    it.c = A.offset + (rem - it.d * A.ncols);
+    it.u = uu + (uu >= it.v ? 1 : 0);
+    return it;
+}
+
+// urow (J_PAIR_VAR only, optional): the partner curve's whole row, already in shared memory.
+// scratch (J_PAIR_VAR only, optional): 2n+1 doubles of shared memory private to the lane (may alias
+// the urow region of the warp: every lane has read its row before anyone writes).  With it the
+// Bernstein product uses that delta = +-e_c is one-hot: s[i + c] = w[i][c] * (u_i * sg) -- the same
+// bits as the dense double loop (all its other terms add +-0), 22 instead of 242 fp64 instructions.
 template <int N_, int DIM, int JMODE>
 __device__ __forceinline__ void jac_stage1(const JacArgs &A, const FullWeights<N_> &FW,
                                            const DiffWeights<N_> &DW, long long item,
-                                           double (&s)[2 * N_ + 1], long long &ro) {
+                                           double (&s)[2 * N_ + 1], long long &ro, const double *urow = nullptr,
+                                           double *scratch = nullptr) {
     constexpr int NC = N_ + 1;
     constexpr int S = (DIM * NC + 1) / 2 * 2;
     constexpr bool DIRMODE = (JMODE == J_PAIR_DIR || JMODE == J_SPEED_DIR);
@@ -62,22 +83,33 @@ __device__ __forceinline__ void jac_stage1(const JacArgs &A, const FullWeights<N
     const int dim_ncols = DIM * A.ncols;
     double a[ND][NC], dl[ND][NC];
     double dxk;
+    int c_hot = 0;              // J_PAIR_VAR: delta = sg_hot * e_{c_hot}
+    double sg_hot = 0.0;
     if (JMODE == J_PAIR_VAR) {
-        const long long kk = item / (A.N - 1);
-        const int uu = (int)(item - kk * (A.N - 1));
-        const int v = (int)(kk / dim_ncols);
-        const int rem = (int)(kk - (long long)v * dim_ncols);
-        const int d = rem / A.ncols;
-        const int c = A.offset + (rem - d * A.ncols);
-        const int u = uu + (uu >= v ? 1 : 0);
+        const PairVarItem it = pair_var_item(A, DIM, item);
+        const long long kk = it.kk;
+        const int v = it.v, d = it.d, c = it.c, u = it.u;
         const int vi = v < u ? v : u, vj = v < u ? u : v;
         const double sg = v < u ? 1.0 : -1.0;
-        const double *pi = A.cpts + (size_t)vi * S + d * NC;
-        const double *pj = A.cpts + (size_t)vj * S + d * NC;
+        c_hot = c;
+        sg_hot = sg;
+        const double *pv = A.cpts + (size_t)v * S + d * NC;
+        if (urow) {                                 // partner row from shared memory (TMA row fetch)
+            const double *pu = urow + d * NC;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            a[0][k] = __ldg(pi + k) - __ldg(pj + k);
-            dl[0][k] = (k == c) ? sg : 0.0;
+            for (int k = 0; k < NC; ++k) {
+                const double cv = __ldg(pv + k), cu = pu[k];
+                a[0][k] = v < u ? cv - cu : cu - cv;
+                dl[0][k] = (k == c) ? sg : 0.0;
+            }
+        } else {
+            const double *pu = A.cpts + (size_t)u * S + d * NC;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const double cv = __ldg(pv + k), cu = __ldg(pu + k);
+                a[0][k] = v < u ? cv - cu : cu - cv;
+                dl[0][k] = (k == c) ? sg : 0.0;
+            }
         }
         dxk = __ldg(A.dx + kk);
         const long long p = bez_pair_row_offset(vi, A.N) + (vj - vi - 1);
@@ -153,6 +185,19 @@ __device__ __forceinline__ void jac_stage1(const JacArgs &A, const FullWeights<N
         ro = A.dense ? (long long)A.kdir * A.ld + (long long)v * A.L : item * (long long)A.L;
     }
 
+    if (JMODE == J_PAIR_VAR && scratch != nullptr) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k <= 2 * N_; ++k) scratch[k] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const double ui = fma(dxk, dl[0][i], 2.0 * a[0][i]);
+            scratch[i + c_hot] = fma(FW.w[i * NC + c_hot], ui * sg_hot, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k <= 2 * N_; ++k) s[k] = scratch[k];
+        return;
+    }
     // s = B(2a + dx*delta, delta)   (Bernstein product, full weight matrix)
 #pragma unroll
     for (int k = 0; k <= 2 * N_; ++k) s[k] = 0.0;
@@ -248,7 +293,8 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
         {
             double s[2 * N_ + 1];
             long long ro;
-            jac_stage1<N_, DIM, JMODE>(A, FW, DW, t0 + (lane < cnt ? lane : cnt - 1), s, ro);
+            jac_stage1<N_, DIM, JMODE>(A, FW, DW, t0 + (lane < cnt ? lane : cnt - 1), s, ro, nullptr,
+                                       rows + lane * kRowStride);
             double *row = rows + lane * kRowStride;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
@@ -257,6 +303,12 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
                 row[slot_o(j)] = lo - hi;
             }
             row[slot_e(N_)] = s[N_] * A.scale;
+            if (JMODE == J_PAIR_VAR) {       // the scratch use of the row overwrote the padding slots of the k-steps
+#pragma unroll
+                for (int j = N_ + 1; j < 4 * Geom<N_>::KE; ++j) row[slot_e(j)] = 0.0;
+#pragma unroll
+                for (int j = N_; j < 4 * Geom<N_>::KO; ++j) row[slot_o(j)] = 0.0;
+            }
         }
         __syncwarp();
         mma_tile<N_, 4, 0, true>(rows, obuf, obuf_s, Bf, A.out + (size_t)t0 * A.L, no_sinks, t0, cnt, A.L, 0.0, lane,
@@ -278,16 +330,20 @@ jac_sq_elev_ws_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeigh
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int group = warp & 3;
-    double *slots = smem + (size_t)group * kSlots * kRowsDoubles;
-    double *stag0 = smem + (size_t)4 * kSlots * kRowsDoubles;
+    constexpr bool TMAROWS = (JMODE == J_PAIR_VAR);
+    constexpr int S_ = (DIM * (N_ + 1) + 1) / 2 * 2;
+    constexpr int kSlotD = TMAROWS ? slot_doubles<N_, DIM>() : kRowsDoubles;
+    double *slots = smem + (size_t)group * kSlots * kSlotD;
+    double *stag0 = smem + (size_t)4 * kSlots * kSlotD;
     const size_t stag_per = 16 * (size_t)A.L;
     const unsigned bars_s = (unsigned)__cvta_generic_to_shared(stag0 + kConsumers * stag_per) + 8u * kBarsPerGroup * group;
     auto full_b = [&](int s) { return bars_s + 8u * s; };
     auto empty_b = [&](int s) { return bars_s + 8u * (kSlots + s); };
+    auto rows_b = [&](int s) { return bars_s + 8u * (2 * kSlots + s); };
     if (warp < kProducers) {
-        for (int i = lane; i < kSlots * kRowsDoubles; i += 32) slots[i] = 0.0;     // padding slots must be 0
+        for (int i = lane; i < kSlots * kSlotD; i += 32) slots[i] = 0.0;           // padding slots must be 0
         if (lane == 0) {
-            for (int s = 0; s < kSlots; ++s) { mbar_init(full_b(s), 32); mbar_init(empty_b(s), 32); }
+            for (int s = 0; s < kSlots; ++s) { mbar_init(full_b(s), 32); mbar_init(empty_b(s), 32); mbar_init(rows_b(s), 1); }
             mbar_fence_init();
         }
     }
@@ -304,9 +360,39 @@ jac_sq_elev_ws_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeigh
             const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
             double sc[2 * N_ + 1];
             long long ro;
-            jac_stage1<N_, DIM, JMODE>(A, FW, DW, t0 + (lane < cnt ? lane : cnt - 1), sc, ro);
-            if (use > 0) mbar_wait(empty_b(s), (unsigned)(use - 1) & 1u);
-            double *row = slots + (size_t)s * kRowsDoubles + lane * kRowStride;
+            const long long item = t0 + (lane < cnt ? lane : cnt - 1);
+            double *slot = slots + (size_t)s * kSlotD;
+            if (TMAROWS) {
+                // the partner rows of a tile are consecutive rows of the control-point array (one run
+                // per variable, broken once at the owner vehicle): one TMA bulk copy per run
+                const PairVarItem it = pair_var_item(A, DIM, item);
+                // the owner's row and the step length go to L1 while the slot is awaited and the rows fly
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(A.cpts + (size_t)it.v * S_ + it.d * (N_ + 1)));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(A.cpts + (size_t)it.v * S_ + it.d * (N_ + 1) + N_));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(A.dx + it.kk));
+                if (use > 0) mbar_wait(empty_b(s), (unsigned)(use - 1) & 1u);
+                const int pu = __shfl_up_sync(0xffffffffu, it.u, 1);
+                const bool start = lane == 0 || it.u != pu + 1;
+                const unsigned runs = __ballot_sync(0xffffffffu, start);
+                const unsigned slot_s = (unsigned)__cvta_generic_to_shared(slot);
+                fence_async_smem();
+                if (lane == 0) mbar_arrive_expect_tx(rows_b(s), 32u * S_ * 8u);
+                __syncwarp();
+                if (start) {
+                    const unsigned higher = lane == 31 ? 0u : (runs & (0xffffffffu << (lane + 1)));
+                    const int end = higher ? __ffs(higher) - 1 : 32;
+                    // a run never leaves the array: rows u .. u + len - 1 <= N - 1 (dead lanes repeat the last item)
+                    bulk_load(slot_s + (unsigned)lane * (S_ * 8u), A.cpts + (size_t)it.u * S_,
+                              (unsigned)(end - lane) * (S_ * 8u), rows_b(s));
+                }
+                mbar_wait(rows_b(s), (unsigned)use & 1u);
+                jac_stage1<N_, DIM, JMODE>(A, FW, DW, item, sc, ro, slot + lane * S_, slot + lane * kRowStride);
+                __syncwarp();
+            } else {
+                jac_stage1<N_, DIM, JMODE>(A, FW, DW, item, sc, ro);
+                if (use > 0) mbar_wait(empty_b(s), (unsigned)(use - 1) & 1u);
+            }
+            double *row = slot + lane * kRowStride;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
                 const double lo = sc[j] * A.scale, hi = sc[2 * N_ - j] * A.scale;
@@ -314,6 +400,12 @@ jac_sq_elev_ws_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeigh
                 row[slot_o(j)] = lo - hi;
             }
             row[slot_e(N_)] = sc[N_] * A.scale;
+            if (TMAROWS) {
+#pragma unroll
+                for (int j = N_ + 1; j < 4 * Geom<N_>::KE; ++j) row[slot_e(j)] = 0.0;
+#pragma unroll
+                for (int j = N_; j < 4 * Geom<N_>::KO; ++j) row[slot_o(j)] = 0.0;
+            }
             mbar_arrive(full_b(s));
         }
     } else {
@@ -332,7 +424,7 @@ jac_sq_elev_ws_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeigh
             const int cnt = (int)((A.nitems - t0) < 32 ? (A.nitems - t0) : 32);
             mbar_wait(full_b(s), (unsigned)use & 1u);
             auto release = [&]() { mbar_arrive(empty_b(s)); };
-            mma_tile<N_, 4, 0, true, decltype(release)>(slots + (size_t)s * kRowsDoubles, obuf, obuf_s, Bf,
+            mma_tile<N_, 4, 0, true, decltype(release)>(slots + (size_t)s * kSlotD, obuf, obuf_s, Bf,
                                                         A.out + (size_t)t0 * A.L, no_sinks, t0, cnt, A.L, 0.0, lane,
                                                         base_aligned, false, release);
             __syncwarp();
@@ -341,14 +433,18 @@ jac_sq_elev_ws_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeigh
     }
 }
 
+template <int N_, int DIM, int JMODE> size_t jac_ws_shmem(int L) {
+    const size_t slot = (JMODE == J_PAIR_VAR) ? bezws::slot_doubles<N_, DIM>() : bezmma::kRowsDoubles;
+    return ((size_t)4 * bezws::kSlots * slot + (size_t)bezws::kConsumers * 16 * L + 4 * bezws::kBarsPerGroup) * sizeof(double);
+}
+
 template <int N_, int DIM, int JMODE>
 int launch_jac_ws(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
     FullWeights<N_> FW;
     DiffWeights<N_> DW;
     for (int i = 0; i < (N_ + 1) * (N_ + 1); ++i) FW.w[i] = plan->h_W[i];
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
-    const size_t shmem = ((size_t)4 * bezws::kSlots * bezmma::kRowsDoubles + (size_t)bezws::kConsumers * 16 * A.L +
-                          4 * bezws::kBarsPerGroup) * sizeof(double);
+    const size_t shmem = jac_ws_shmem<N_, DIM, JMODE>(A.L);
     auto kern = jac_sq_elev_ws_kernel<N_, DIM, JMODE>;
     int sms = 148, per_sm = 1;
     if (int rc = bez_kernel_config((const void *)kern, bezws::kWsThreads, shmem, &sms, &per_sm)) return rc;
@@ -367,11 +463,14 @@ int launch_jac_mma(const bez_plan *plan, const JacArgs &A, cudaStream_t st) {
     DiffWeights<N_> DW;
     for (int i = 0; i < (N_ + 1) * (N_ + 1); ++i) FW.w[i] = plan->h_W[i];
     for (int i = 0; i <= N_; ++i) { DW.lo[i] = plan->h_E1lo[i]; DW.hi[i] = plan->h_E1hi[i]; }
-    const size_t ws_shmem = ((size_t)4 * bezws::kSlots * bezmma::kRowsDoubles + (size_t)bezws::kConsumers * 16 * A.L +
-                             4 * bezws::kBarsPerGroup) * sizeof(double);
-    // measured (tools/prof_jac.py): 7.1 ms against 5.0 ms -- one producer cannot feed two consumers here, its stage 1
-    // waits for scattered global loads tile after tile; kept behind BEZGPU_MMA_FLAGS bit 256 as an experiment
-    if (ws_shmem <= 232448 && (bez_sq_elev_mma_flags() & 256)) return launch_jac_ws<N_, DIM, JMODE>(plan, A, st);
+    const size_t ws_shmem = jac_ws_shmem<N_, DIM, JMODE>(A.L);
+    // Per-variable separation sweep (the 27 GB block of the C4 Jacobian): warp-specialised with a TMA fetch of the
+    // partner rows (tools/prof_jac.py: 4.72-4.76 ms in bursts of four launches, 4.39 ms = 0.96 of the HBM peak for an
+    // isolated launch under ncu; the 8-warp kernel 4.90 ms).  Without the row fetch (the other modes) one producer
+    // cannot feed two consumers -- its stage 1 waits for scattered global loads tile after tile (7.1 ms) -- so they
+    // stay on the 8-warp kernel.  BEZGPU_MMA_FLAGS bit 128 keeps everything there (A/B).
+    if (JMODE == J_PAIR_VAR && ws_shmem <= 232448 && !(bez_sq_elev_mma_flags() & kFlagNoWarpSpecialisation))
+        return launch_jac_ws<N_, DIM, JMODE>(plan, A, st);
     const size_t shmem = (size_t)kWarps * (bezmma::kRowsDoubles + 16 * (size_t)A.L) * sizeof(double);
     auto kern = jac_sq_elev_mma_kernel<N_, DIM, JMODE>;
     int sms = 148, per_sm = 1;

@@ -165,7 +165,8 @@ int launch_sq_elev_ws(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st
     const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
     long long grid = sms;
     if (grid > (nwt + 7) / 8) grid = (nwt + 7) / 8;
-    if (A.sinks.npeers > 0 && grid == sms && grid > 1 && !(A.flags & kFlagFullGridWithPeers)) grid -= 1;
+    if ((A.sinks.npeers > 0 || (A.flags & kFlagLeaveOneSm)) && grid == sms && grid > 1 && !(A.flags & kFlagFullGridWithPeers))
+        grid -= 1;
     if (grid < 1) return BEZ_OK;
     kern<<<(unsigned)grid, kWsThreads, shmem, st>>>(A, PW, DW);
     BEZ_CUDA(cudaGetLastError());
