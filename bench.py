@@ -328,7 +328,9 @@ def run_ours(opts):
     # pair kernel (NVLink peer stores into symmetric memory, sharding.PeerMinima); fallback:
     # NCCL all-gather on its own stream.
     gatherer, peer, gather_mode = None, None, "none (1 GPU)"
-    if world > 1 and not opts.nccl_gather:
+    if world > 1 and opts.no_gather:       # diagnostic: N independent replicas, no exchange at all
+        gather_mode = "none (diagnostic --no-gather)"
+    if world > 1 and not opts.nccl_gather and not opts.no_gather:
         try:
             peer = sharding.PeerMinima(B, P, eng.device, layout="pairs" if strong else "batch")
             gather_mode = ("fused: in-kernel NVLink %s into symmetric memory; signal-pad barrier on a "
@@ -337,7 +339,7 @@ def run_ours(opts):
         except Exception as e:                      # symmetric memory not available on this box
             if rank == 0:
                 print("PeerMinima unavailable (%r); falling back to NCCL all-gather" % (e,), file=sys.stderr)
-    if peer is None and not strong:
+    if peer is None and not strong and not opts.no_gather:
         gatherer = sharding.PairMinimaGatherer(B, P, eng.device)
         if world > 1:
             gather_mode = "NCCL all_gather_into_tensor on a side stream"
@@ -354,12 +356,20 @@ def run_ours(opts):
                 pm, peers = peer.targets()
                 eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=osep, pairmin=pm,
                                peer_ptrs=peers, min_pitch=P if strong else None)
+                # the completion barrier covers the pair kernel's peer stores only: issued behind it, not behind
+                # the speed kernel -- that one finds no SM until the NEXT persistent pair kernel (already queued on
+                # the other launch stream) drains, and a barrier behind it would reach step k+2 a whole kernel late
+                gathered = peer.complete()
                 eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=ospd)
-                return peer.complete(), osep
+                return gathered, osep
             if strong:
                 eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=osep, pairmin=opm)
                 eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=ospd)
                 return sharding.gather_pair_minima(opm, mode="pairs", total=P), osep
+            if gatherer is None:
+                eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=opm)
+                eng.speed(cpts, tf, E, -1.0, max_speed2, out=ospd)
+                return opm, osep
             pm = gatherer.local_buffer()
             eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=pm)
             eng.speed(cpts, tf, E, -1.0, max_speed2, out=ospd)
@@ -411,7 +421,7 @@ def run_ours(opts):
     ev1.record()
     barrier()
     ms = maxreduce(ev0.elapsed_time(ev1))
-    if world > 1:
+    if world > 1 and not opts.no_gather:
         # self-check of the collective (outside the timed region): the gathered matrix of the
         # last step must equal a plain NCCL all-gather of the per-rank minima, bit for bit
         mine = last_sep.min(dim=2).values.contiguous()
@@ -880,6 +890,8 @@ def main():
     ap.add_argument("--nccl-gather", action="store_true",
                     help="multi-GPU: use the NCCL all-gather instead of the fused in-kernel peer stores")
     ap.add_argument("--no-sweep", action="store_true", help="skip the closed-form Jacobian sweep leg")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="diagnostic: with N > 1 run N independent replicas without the all-gather of the per-pair minima")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4 = the headline swarm (default); c5 = batch of independent Dubins problems")
     ap.add_argument("--problems", type=int, default=8192, help="c5: problems per GPU")
