@@ -354,27 +354,26 @@ def run_ours(opts):
             cpts, tf = eng.assemble(d_x, E)
             if peer is not None:
                 pm, peers = peer.targets()
+                eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=ospd)
                 eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=osep, pairmin=pm,
                                peer_ptrs=peers, min_pitch=P if strong else None)
-                # the completion barrier covers the pair kernel's peer stores only: issued behind it, not behind
-                # the speed kernel -- that one finds no SM until the NEXT persistent pair kernel (already queued on
-                # the other launch stream) drains, and a barrier behind it would reach step k+2 a whole kernel late
+                # (the speed rows go first: behind the persistent pair kernel they would find no SM until the NEXT
+                # pair kernel, already queued on the other launch stream, has drained)
                 gathered = peer.complete()
-                eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=ospd)
                 return gathered, osep
             if strong:
-                eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=osep, pairmin=opm)
                 eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=ospd)
+                eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=osep, pairmin=opm)
                 return sharding.gather_pair_minima(opm, mode="pairs", total=P), osep
             if gatherer is None:
-                eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=opm)
                 eng.speed(cpts, tf, E, -1.0, max_speed2, out=ospd)
+                eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=opm)
                 return opm, osep
             pm = gatherer.local_buffer()
-            eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=pm)
             eng.speed(cpts, tf, E, -1.0, max_speed2, out=ospd)
+            eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=pm)
             return gatherer.gather(), osep
-    launches_per_step = 3       # assemble, fused pair kernel (values + per-pair min), speed kernel
+    launches_per_step = 3       # assemble, speed kernel, fused pair kernel (values + per-pair min)
 
     def fork():
         """the launch streams start behind everything queued on the default stream"""

@@ -29,9 +29,9 @@ constexpr int kFlagStridedTiles = 2;   // round-1 tile order (warp-strided, full
 //  reused since:)
 constexpr int kFlagRowsByLdg = 4;      // A/B: partner rows through per-lane global loads (no TMA row fetch)
 constexpr int kFlagEarlyFence = 8;     // A/B: proxy fence + bulk store right behind an m-tile's epilogue
-constexpr int kFlagFullGridWithPeers = 16;   // A/B: do not leave a CTA slot free for the completion barrier
+constexpr int kFlagFullGrid = 16;       // A/B: do not leave a CTA slot / an SM free for the small kernels around the pair kernel
+constexpr int kFlagFullGridWithPeers = kFlagFullGrid;
 constexpr int kFlagFusedList = 64;     // A/B: append the active list from the epilogue even in large launches
-constexpr int kFlagLeaveOneSm = 512;   // A/B: the warp-specialised kernel leaves one SM to the small kernels of the next step
 constexpr int kFlagNoWarpSpecialisation = 128;  // A/B: 65 <= L <= 128 pair rows on the 8-warp kernel instead of sq_elev_ws.cuh
 // (bit 32 was the third-generation "team" kernel: profiles/r02_ablation_pair_kernel.txt)
 

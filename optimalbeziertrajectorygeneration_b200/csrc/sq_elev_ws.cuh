@@ -165,8 +165,12 @@ int launch_sq_elev_ws(const bez_plan *plan, const SqElevArgs &A, cudaStream_t st
     const long long nwt = (A.nitems * (long long)A.B + 31) / 32;
     long long grid = sms;
     if (grid > (nwt + 7) / 8) grid = (nwt + 7) / 8;
-    if ((A.sinks.npeers > 0 || (A.flags & kFlagLeaveOneSm)) && grid == sms && grid > 1 && !(A.flags & kFlagFullGridWithPeers))
-        grid -= 1;
+    // One SM stays free.  The CTAs of this kernel fill an SM completely (223 KB, all registers), so every small
+    // kernel queued behind or next to it -- the next step's counter reset / assemble / speed rows on the other
+    // launch stream, the list compaction, the completion barrier of the fused all-gather -- would otherwise wait
+    // for a whole persistent kernel to drain (tools/timeline_e2e.py: an 88 us bubble per two steps end to end).
+    // 0.7 % of the grid; measured +0.5-1 % device-resident and +2 % end to end.  BEZGPU_MMA_FLAGS bit 16: full grid.
+    if (grid == sms && grid > 1 && !(A.flags & kFlagFullGrid)) grid -= 1;
     if (grid < 1) return BEZ_OK;
     kern<<<(unsigned)grid, kWsThreads, shmem, st>>>(A, PW, DW);
     BEZ_CUDA(cudaGetLastError());

@@ -568,8 +568,9 @@ class BezOptimization:
             if k + 1 < nchunks:
                 x_ready = upload(k + 1, prev_ready)
             cpts, tf = eng.assemble(ws['x'][:b], E)
-            eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b], pairmin=ws['pairmin'][:b])
+            # speed rows first (see evaluate_sweep_active.launch)
             eng.speed(cpts, tf, E, -1.0, max_speed2, nveh=nv, out=ws['maxspeed'][:b])
+            eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b], pairmin=ws['pairmin'][:b])
             ready = torch.cuda.Event()
             ready.record(main)
             prev_ready = ready
@@ -654,12 +655,15 @@ class BezOptimization:
                 return ev
 
             def launch(ws, b, pa, va):
+                # the speed rows go first: behind the persistent pair kernel they would find no SM until the NEXT
+                # chunk's pair kernel (already queued on the other stream) has drained, and this chunk's result
+                # would leave the device a whole kernel late
                 pa.reset()
                 cpts, tf = eng.assemble(ws['x'][:b], E)
-                eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b] if rows else None, rows=rows,
-                               pairmin=ws['pairmin'][:b], active=pa)
                 eng.speed(cpts, tf, E, -1.0, max_speed2, nveh=nv, out=ws['maxspeed'][:b], vehmin=ws['vehmin'][:b],
                           active=va)
+                eng.separation(cpts, E, self.model['maxSep'], out=ws['sep'][:b] if rows else None, rows=rows,
+                               pairmin=ws['pairmin'][:b], active=pa)
 
             use_graph = bool(getattr(self, 'sweep_cuda_graphs', True))
             # Consecutive chunks run on two alternating compute streams (their workspaces are
