@@ -68,6 +68,7 @@ class ClockSampler:
         self.gpu, self.period = gpu_index, period
         self.sm, self.reasons, self.smax = [], set(), None
         self._stop = threading.Event()
+        self._go = threading.Event()
         self.thread = None
         self.err = None
 
@@ -86,7 +87,8 @@ class ClockSampler:
     def _run(self):
         try:
             pynvml, h = self._nvml, self._h
-            while True:
+            self._go.wait()                # armed by go(): the first sample belongs to the timed region
+            while not self._stop.is_set():
                 self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                 try:
                     mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -108,16 +110,25 @@ class ClockSampler:
         except Exception as e:            # pragma: no cover
             self.err = repr(e)
 
-    def start(self):
+    def start(self, armed=True):
+        """Starts the sampling thread.  With armed=False the thread is created (hundreds of microseconds on
+        rank 0 only -- with a fused all-gather every rank's timed region absorbs that start skew) but samples
+        nothing until go() is called right in front of the timed region."""
         if self.err is None and not hasattr(self, "_h"):
             self.open()
         if self.err is not None:
             return
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+        if armed:
+            self._go.set()
+
+    def go(self):
+        self._go.set()
 
     def stop(self):
         self._stop.set()
+        self._go.set()
         if self.thread is not None:
             self.thread.join(timeout=5)
         out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
@@ -316,6 +327,20 @@ def run_ours(opts):
     # its CTAs fill the SMs as they free up (no launch gap, no idle tail between steps).
     nlanes = 1 if opts.single_stream else 2
     lanes = [torch.cuda.Stream(device=eng.device) for _ in range(nlanes)]
+    # the speed rows of a step only need the assembled control points: they run on a side stream of their launch
+    # stream, next to (in practice: at the tail of) the previous persistent pair kernel, and never in front of
+    # their own step's pair kernel
+    aux = [torch.cuda.Stream(device=eng.device) for _ in range(nlanes)]
+
+    def speed_aside(i, cpts, tf, ospd, **kw):
+        ready = torch.cuda.Event()
+        ready.record(lanes[i])
+        with torch.cuda.stream(aux[i]):
+            aux[i].wait_event(ready)
+            eng.speed(cpts, tf, E, -1.0, max_speed2, out=ospd, **kw)
+            done = torch.cuda.Event()
+            done.record(aux[i])
+        return done
     out_seps = [torch.empty((B, Pr, L), dtype=torch.float64, device=eng.device) for _ in range(nlanes)]
     out_spds = [torch.empty((B, Nr, L), dtype=torch.float64, device=eng.device) for _ in range(nlanes)]
     pairmins = [torch.empty((B, Pr), dtype=torch.float64, device=eng.device) for _ in range(nlanes)]
@@ -354,24 +379,28 @@ def run_ours(opts):
             cpts, tf = eng.assemble(d_x, E)
             if peer is not None:
                 pm, peers = peer.targets()
-                eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=ospd)
+                sdone = speed_aside(i, cpts, tf, ospd, veh_begin=v_lo, nveh=Nr)
                 eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=osep, pairmin=pm,
                                peer_ptrs=peers, min_pitch=P if strong else None)
+                lanes[i].wait_event(sdone)
                 # (the speed rows go first: behind the persistent pair kernel they would find no SM until the NEXT
                 # pair kernel, already queued on the other launch stream, has drained)
                 gathered = peer.complete()
                 return gathered, osep
             if strong:
-                eng.speed(cpts, tf, E, -1.0, max_speed2, veh_begin=v_lo, nveh=Nr, out=ospd)
+                sdone = speed_aside(i, cpts, tf, ospd, veh_begin=v_lo, nveh=Nr)
                 eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=osep, pairmin=opm)
+                lanes[i].wait_event(sdone)
                 return sharding.gather_pair_minima(opm, mode="pairs", total=P), osep
             if gatherer is None:
-                eng.speed(cpts, tf, E, -1.0, max_speed2, out=ospd)
+                sdone = speed_aside(i, cpts, tf, ospd)
                 eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=opm)
+                lanes[i].wait_event(sdone)
                 return opm, osep
             pm = gatherer.local_buffer()
-            eng.speed(cpts, tf, E, -1.0, max_speed2, out=ospd)
+            sdone = speed_aside(i, cpts, tf, ospd)
             eng.separation(cpts, E, args["maxSep"], out=osep, pairmin=pm)
+            lanes[i].wait_event(sdone)
             return gatherer.gather(), osep
     launches_per_step = 3       # assemble, speed kernel, fused pair kernel (values + per-pair min)
 
@@ -408,17 +437,33 @@ def run_ours(opts):
     sampler = ClockSampler(local, period=opts.clock_period)
     if rank == 0:
         sampler.open()
+        sampler.start(armed=False)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.go()
+    prof = None
+    if opts.timeline and rank == 0:        # diagnostic: CUPTI kernel timeline of the timed region (distorts the timing)
+        from torch.profiler import ProfilerActivity, profile
+        prof = profile(activities=[ProfilerActivity.CUDA])
+        prof.__enter__()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     fork()
+    t_host0 = time.perf_counter()
     for _ in range(opts.steps):
         gathered, last_sep = step()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / opts.steps     # host time to enqueue one step
     finish()
     ev1.record()
     barrier()
+    if prof is not None:
+        prof.__exit__(None, None, None)
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                     key=lambda e: e.time_range.start)
+        with open(opts.timeline, "w") as f:
+            for e in evs:
+                f.write("%10.1f us  +%8.1f us  %s\n" % (e.time_range.start - evs[0].time_range.start,
+                                                         e.time_range.end - e.time_range.start, e.name[:90]))
     ms = maxreduce(ev0.elapsed_time(ev1))
     if world > 1 and not opts.no_gather:
         # self-check of the collective (outside the timed region): the gathered matrix of the
@@ -437,6 +482,14 @@ def run_ours(opts):
     torch.cuda.synchronize()
     kms = _time_events(lambda: eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=out_sep,
                                               pairmin=pairmin), opts.steps, torch)
+    # ... and with the fused all-gather's peer / multicast stores (no barrier): what the exchange costs inside the kernel
+    kms_peer = None
+    if peer is not None:
+        pm_, peers_ = peer.targets()
+        kms_peer = _time_events(lambda: eng.separation(cpts, E, args["maxSep"], pair_begin=p_lo, npairs=Pr, out=out_sep,
+                                                       pairmin=pm_, peer_ptrs=peers_, min_pitch=P if strong else None),
+                                opts.steps, torch)
+        barrier()
     # the same kernel in the production launch pattern: back-to-back launches alternating between the
     # two launch streams, so that the CTAs of launch k+1 fill the SMs as launch k drains
     kms_pipe = None
@@ -478,14 +531,16 @@ def run_ours(opts):
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "kernel": "sq_elev_ws_kernel<10,3,min,rows>: warp-specialised pair kernel (producer warps: TMA row "
                                        "fetch + stage 1; consumer warps: DMMA.8x8x4 stage 2, fused minimum, TMA bulk-store epilogue)",
-                             "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                             "kernel_ms": kms, "kernel_ms_with_peer_stores": kms_peer,
+                             "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                              "pipelined": None if kms_pipe is None else {
                                  "ms_per_launch": kms_pipe, "achieved": alg_bytes / (kms_pipe * 1e-3) / 1e9,
                                  "frac": alg_bytes / (kms_pipe * 1e-3) / 1e9 / peak,
                                  "note": "same kernel, back-to-back launches alternating between two streams (the "
                                          "production launch pattern of the step loop): total time / launches; "
                                          "`frac` above is the conservative figure from isolated launches"}},
-                "gpu_launches": launches_per_step * opts.steps, "clocks": clocks}
+                "gpu_launches": launches_per_step * opts.steps, "clocks": clocks,
+                "host_enqueue_ms_per_step": host_enqueue_ms}
         if strong:
             line["config"] = dict(workload_config(), sharding="one FD batch; the pair list cut into contiguous "
                                   "ranges per rank (vehicle blocks for the speed rows); fused gather into one [B,P] matrix")
@@ -889,6 +944,7 @@ def main():
     ap.add_argument("--nccl-gather", action="store_true",
                     help="multi-GPU: use the NCCL all-gather instead of the fused in-kernel peer stores")
     ap.add_argument("--no-sweep", action="store_true", help="skip the closed-form Jacobian sweep leg")
+    ap.add_argument("--timeline", default=None, help="diagnostic: write the kernel timeline of the timed region to this file")
     ap.add_argument("--no-gather", action="store_true",
                     help="diagnostic: with N > 1 run N independent replicas without the all-gather of the per-pair minima")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],

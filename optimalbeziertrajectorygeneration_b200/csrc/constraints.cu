@@ -119,19 +119,23 @@ struct AssembleArgs {
     double *cpts, *tf;
 };
 
+// IdxT = unsigned when the element count fits 32 bits (every BASELINE config): the index decomposition
+// is four divisions per element, and 64-bit ones made this kernel take 200 us on the single SM the
+// persistent pair kernel leaves to the small kernels of the next step (3 us on an empty GPU).
+template <typename IdxT>
 __global__ void assemble_cpts_kernel(const AssembleArgs A) {
     const int NC = A.n + 1;
     const int N = A.numVeh + A.nObs;
     const int S = (A.dim * NC + 1) / 2 * 2;
-    const long long total = (long long)A.B * N * S;
+    const IdxT total = (IdxT)A.B * (IdxT)N * (IdxT)S;
     const int offset = (A.fixed_ends ? 1 : 0) + (A.dubins ? 1 : 0);
     const int ncols = NC - 2 * offset;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int e = (int)(idx % S);
-        const long long r = idx / S;
-        const int v = (int)(r % N);
-        const int b = (int)(r / N);
+    for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (IdxT)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % (IdxT)S);
+        const IdxT r = idx / (IdxT)S;
+        const int v = (int)(r % (IdxT)N);
+        const int b = (int)(r / (IdxT)N);
         if (e >= A.dim * NC) { A.cpts[idx] = 0.0; continue; }          // alignment pad
         const int d = e / NC, k = e - d * NC;
         const double *x = A.x + (size_t)b * A.nvar;
@@ -479,7 +483,10 @@ extern "C" int bez_assemble_cpts_sets(const bez_plan *plan, const double *d_x, i
     const long long total = (long long)B * (numVeh + nObs) * S;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    assemble_cpts_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
+    if (total + 148LL * 16 * 256 < 0xffffffffLL)
+        assemble_cpts_kernel<unsigned><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
+    else
+        assemble_cpts_kernel<long long><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
     BEZ_CUDA(cudaGetLastError());
     return BEZ_OK;
 }
