@@ -67,11 +67,11 @@ __device__ __forceinline__ PairVarItem pair_var_item(const JacArgs &A, int dim, 
 }
 
 // urow (J_PAIR_VAR only, optional): the partner curve's whole row, already in shared memory.
-// scratch (J_PAIR_VAR only, optional): 2n+1 doubles of shared memory private to the lane (may alias
+// ONEHOT + scratch (J_PAIR_VAR only): 2n+1 doubles of shared memory private to the lane (may alias
 // the urow region of the warp: every lane has read its row before anyone writes).  With it the
 // Bernstein product uses that delta = +-e_c is one-hot: s[i + c] = w[i][c] * (u_i * sg) -- the same
 // bits as the dense double loop (all its other terms add +-0), 22 instead of 242 fp64 instructions.
-template <int N_, int DIM, int JMODE>
+template <int N_, int DIM, int JMODE, bool ONEHOT = false>
 __device__ __forceinline__ void jac_stage1(const JacArgs &A, const FullWeights<N_> &FW,
                                            const DiffWeights<N_> &DW, long long item,
                                            double (&s)[2 * N_ + 1], long long &ro, const double *urow = nullptr,
@@ -185,7 +185,7 @@ __device__ __forceinline__ void jac_stage1(const JacArgs &A, const FullWeights<N
         ro = A.dense ? (long long)A.kdir * A.ld + (long long)v * A.L : item * (long long)A.L;
     }
 
-    if (JMODE == J_PAIR_VAR && scratch != nullptr) {
+    if (ONEHOT && JMODE == J_PAIR_VAR) {
         __syncwarp();
 #pragma unroll
         for (int k = 0; k <= 2 * N_; ++k) scratch[k] = 0.0;
@@ -293,8 +293,8 @@ jac_sq_elev_mma_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeig
         {
             double s[2 * N_ + 1];
             long long ro;
-            jac_stage1<N_, DIM, JMODE>(A, FW, DW, t0 + (lane < cnt ? lane : cnt - 1), s, ro, nullptr,
-                                       rows + lane * kRowStride);
+            jac_stage1<N_, DIM, JMODE, JMODE == J_PAIR_VAR>(A, FW, DW, t0 + (lane < cnt ? lane : cnt - 1), s, ro, nullptr,
+                                                            rows + lane * kRowStride);
             double *row = rows + lane * kRowStride;
 #pragma unroll
             for (int j = 0; j < N_; ++j) {
@@ -386,7 +386,7 @@ jac_sq_elev_ws_kernel(const JacArgs A, const FullWeights<N_> FW, const DiffWeigh
                               (unsigned)(end - lane) * (S_ * 8u), rows_b(s));
                 }
                 mbar_wait(rows_b(s), (unsigned)use & 1u);
-                jac_stage1<N_, DIM, JMODE>(A, FW, DW, item, sc, ro, slot + lane * S_, slot + lane * kRowStride);
+                jac_stage1<N_, DIM, JMODE, true>(A, FW, DW, item, sc, ro, slot + lane * S_, slot + lane * kRowStride);
                 __syncwarp();
             } else {
                 jac_stage1<N_, DIM, JMODE>(A, FW, DW, item, sc, ro);
